@@ -1,0 +1,149 @@
+/* neuroclear_b200 — C ABI of the B200 (sm_100a) hot path of peterhpark/neuroclear.
+ *
+ * The reference is pure Python (no FFI of its own), so this header IS the drop-in boundary: the Python shims
+ * in neuroclear_b200/ (same class / function names as the reference: networks.define_G('unet_deconv'),
+ * DiceImageDataSet, Assemble_Dice, Volume.get_projection) bind exactly these symbols through ctypes.
+ * Each entry point cites the reference code it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is caller-owned CUDA device memory (e.g. a torch
+ *     tensor's data_ptr()); nothing here allocates persistent device memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, one host thread per
+ *     device; return value 0 = OK, negative = error with the message in nc_last_error() (thread-local).
+ *   - activations between the tensor-core convolutions are bf16, NDHWC ("channels-last-3d"); convolution
+ *     outputs that feed InstanceNorm are raw fp32 NDHWC plus per-tile statistics partials.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with an error.
+ */
+#ifndef NEUROCLEAR_B200_H_
+#define NEUROCLEAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nc_stream_t; /* cudaStream_t */
+
+#define NC_ABI_VERSION 1
+
+/* ---- runtime ------------------------------------------------------------------------------------------- */
+int nc_abi_version(void);
+const char* nc_last_error(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+int nc_device_sm_count(void);
+
+/* ---- dicing geometry (host-only integer math) --------------------------------------------------------------
+ * util/util.py:196-215 pad_for_dicing  +  data/diceImage_dataset.py:82-106 DiceCube.__init__/indexToCoordinates
+ * +  util/assemble_dice.py:21-25,60-77.  size/padded/steps are (z, y, x).  Returns the number of cubes. */
+int64_t nc_dice_geometry(const int32_t size_zyx[3], int32_t roi, int32_t overlap, int32_t padded_zyx[3],
+                         int32_t steps_zyx[3]);
+
+/* ---- dice extraction ------------------------------------------------------------------------------------------
+ * data/diceImage_dataset.py:95-96,108-120 (reflect pad by border + cube slice) fused with
+ * data/base_dataset.py:134-143,291-301 (uint16 / 65535 -> float32, add channel) and the zero far-end padding of
+ * util/util.py:212.  `vol` holds original-volume planes [vol_z0, vol_z0+vol_nz) of a (Z,Y,X) uint16 volume.
+ * Writes cubes [cube_begin, cube_begin+cube_count) as float32 (count, E, E, E), E = roi + 2*border. */
+int nc_dice_extract_u16(const uint16_t* vol /*device*/, int32_t vol_z0, int32_t vol_nz, const int32_t size_zyx[3],
+                        const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                        int32_t border, int64_t cube_begin, int32_t cube_count, float* cubes /*device*/,
+                        nc_stream_t stream);
+
+/* ---- Unet_deconv layers (models/networks.py:478-538) ------------------------------------------------------ */
+
+/* Number of statistics-partial rows a conv writes for a (NB,D,H,W) output with Cout channels; the partial
+ * buffer is float32 [rows][2][Cout] (sum, sum of squares per tile). `cin` selects the kernel (1 = first layer). */
+int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cout);
+
+/* double_conv1.convolution.0 (networks.py:420,490): Conv3d(1 -> Cout, k3 s1 p1), fp32 CUDA-core direct conv.
+ * x: float32 (NB,D,H,W); w: float32 (Cout,1,3,3,3) as stored in the state_dict; Cout must be 64.
+ * y_raw: float32 NDHWC (NB,D,H,W,Cout) WITHOUT bias (a bias in front of InstanceNorm(affine=False) cancels). */
+int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d, int32_t h, int32_t wdt, int32_t cout,
+                          float* y_raw, float* stats_partial, nc_stream_t stream);
+
+/* Packed weight sizes / packing for the tensor-core kernels.  conv: w is OIDHW float32 (Cout,Cin,3,3,3);
+ * convT: w is IODHW float32 (Cin,Cout,2,2,2) (torch ConvTranspose3d layout).  Output is the bf16 swizzled
+ * shared-memory image the kernels stream with bulk copies. */
+int64_t nc_packed_weight_bytes(int32_t cout, int32_t cin, int32_t transposed);
+int nc_pack_weights_conv3d_k3(const float* w_oidhw, int32_t cout, int32_t cin, void* packed, nc_stream_t stream);
+int nc_pack_weights_convT3d_k2s2(const float* w_iodhw, int32_t cin, int32_t cout, void* packed, nc_stream_t stream);
+
+/* nn.Conv3d(Cin -> Cout, k3 s1 p1) of double_conv / triple_conv / last_conv (networks.py:413-476): tcgen05
+ * implicit GEMM, bf16 operands, fp32 accumulate.  x: bf16 NDHWC (NB,D,H,W,Cin) (Cin may be a concat buffer);
+ * y_raw: float32 NDHWC (NB,D,H,W,Cout) without bias; stats_partial as above.  Cin % 64 == 0, Cout in {64,128k}. */
+int nc_conv3d_k3_fwd(const void* x_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
+                     int32_t cout, float* y_raw, float* stats_partial, nc_stream_t stream);
+
+/* nn.ConvTranspose3d(Cin -> Cout, k2 s2) t_conv2 / t_conv1 (networks.py:500,503) fused with the channel concat
+ * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as bf16 into
+ * channels [y_coff, y_coff+Cout) of an NDHWC buffer (NB,2D,2H,2W,y_ld). */
+int nc_convT3d_k2s2_fwd(const void* x_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
+                        const void* packed, const float* bias, int32_t cout, void* y_bf16, int32_t y_ld,
+                        int32_t y_coff, nc_stream_t stream);
+
+/* InstanceNorm3d(affine=False, eps) statistics (networks.py:33-34): deterministic fixed-order reduction of the
+ * per-tile partials in fp64 -> mean_rstd float32 (NB, 2, C): [:,0,:] = mean, [:,1,:] = 1/sqrt(var_biased+eps). */
+int nc_in_stats_finalize(const float* stats_partial, int32_t nb, int64_t rows_per_sample, int32_t c,
+                         int64_t voxels_per_sample, float eps, float* mean_rstd, nc_stream_t stream);
+
+/* InstanceNorm apply + ReLU (+ MaxPool3d(2), networks.py:491,494) + write into a concat slice:
+ * y[..., y_coff:y_coff+C] = bf16(relu((raw - mean) * rstd)); if pooled != NULL also the 2x2x2 max as bf16
+ * NDHWC (NB,D/2,H/2,W/2,C).  raw: float32 NDHWC. */
+int nc_in_relu_apply(const float* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+                     int32_t c, void* y_bf16, int32_t y_ld, int32_t y_coff, void* pooled_bf16, nc_stream_t stream);
+
+/* Tail of Unet_deconv.forward (networks.py:504-510,533-536): InstanceNorm+ReLU of ex_conv1_1, one_by_one (C->1),
+ * one_by_one_2 (1->1) and sigmoid in one pass; optionally drops `crop` voxels per side (the border cut of
+ * util/assemble_dice.py:143).  head_params (device float32): [w1[0..C), b1, w2, b2].
+ * raw: float32 NDHWC (NB,D,H,W,C); y: float32 (NB, D-2crop, H-2crop, W-2crop). */
+int nc_head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* head_params, int32_t nb,
+                            int32_t d, int32_t h, int32_t w, int32_t c, int32_t crop, float* y, nc_stream_t stream);
+
+/* ---- assembly (util/assemble_dice.py:161-213) ---------------------------------------------------------------
+ * Overlap-add blend in the reference's exact fp32 order: for every padded-volume voxel p in planes
+ * [out_z0, out_z0+out_nz): acc = 0; for cubes covering p in ascending cube index: acc += cube[p-origin] * 0.125f;
+ * out = (acc / n(p)) * 8 with n(p) the analytic overlap count (assemble_dice.py:167-184).
+ * Cube outputs are given as "pieces": piece_off[i] = float offset into `pieces` of cube i's stored planes
+ * (-1: cube absent), piece_z0[i] = cube-local z of the first stored plane; each plane is roi*roi floats. */
+int nc_blend_gather_f32(const float* pieces, const int64_t* piece_off, const int32_t* piece_z0,
+                        const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                        int32_t out_z0, int32_t out_nz, float* out, nc_stream_t stream);
+
+/* Exact order statistics for np.percentile (assemble_dice.py:191) by 3-pass radix select over the fp32 bit
+ * pattern (values must be >= 0).  State lives on the device:  sel_state = uint64 rank[4], uint32 prefix[4].
+ *   nc_select_init      : set the (up to 4) zero-based target ranks
+ *   nc_select_histogram : pass in {0,1,2}; adds to hist (uint64 [4][4096]) the counts of the pass's digit for
+ *                         elements matching each target's current prefix (all-reduce hist across GPUs between
+ *                         the two calls when the volume is sharded)
+ *   nc_select_update    : consume hist, narrow prefix/rank; after pass 2 prefix[t] is the value's bit pattern
+ *   nc_percentile_lerp  : numpy's linear-method lerp in fp64 for two percentiles from the four order
+ *                         statistics: out_f64[2] = (p_lo, p_hi), out_f32[3] = (f32(p_lo), f32(p_hi), f32(p_hi - p_lo)) */
+int nc_select_init(const uint64_t ranks[4], void* sel_state, nc_stream_t stream);
+int nc_select_histogram(const float* data, int64_t n, int32_t pass, const void* sel_state, uint64_t* hist,
+                        nc_stream_t stream);
+int nc_select_update(int32_t pass, void* sel_state, uint64_t* hist, nc_stream_t stream);
+int nc_percentile_lerp(const void* sel_state, double t_lo, double t_hi, double* out_f64, float* out_f32,
+                       nc_stream_t stream);
+
+/* skimage.exposure.rescale_intensity(in_range=(p1,p99)) + *65535 + astype(uint16) + un-pad crop
+ * (assemble_dice.py:190-213).  vol: float32 padded planes [vol_z0, ...); writes uint16 planes
+ * [z_begin, z_begin+z_count) of the ORIGINAL (Z,Y,X) volume to `out` (count, Y, X).
+ * norm3 (device float32[3]) = (f32(p1), f32(p99), f32(p99-p1)) as written by nc_percentile_lerp;
+ * NULL => no intensity normalisation. */
+int nc_rescale_u16_crop(const float* vol, int32_t vol_z0, const int32_t padded_zyx[3], const int32_t size_zyx[3],
+                        const float* norm3, int32_t z_begin, int32_t z_count, uint16_t* out, nc_stream_t stream);
+
+/* ---- randomised-depth max-intensity projection (models/axial_to_lateral_gan_apollo_model.py:339-351) ------
+ * vol: float32 (D,H,W) single-channel cube; projects planes [start, start+depth) along `axis` (0=z,1=y,2=x)
+ * with max; fwd also records the arg-max plane (int32) used by bwd to route the gradient
+ * (torch.max(dim)[0] autograd semantics: first maximal index). */
+int nc_mip_fwd(const float* vol, int32_t d, int32_t h, int32_t w, int32_t axis, int32_t start, int32_t depth,
+               float* proj, int32_t* argmax, nc_stream_t stream);
+int nc_mip_bwd(const float* grad_proj, const int32_t* argmax, int32_t d, int32_t h, int32_t w, int32_t axis,
+               float* grad_vol /* accumulated into */, nc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUROCLEAR_B200_H_ */

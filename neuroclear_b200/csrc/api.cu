@@ -1,0 +1,132 @@
+// extern "C" surface of libneuroclear_b200.so — see include/neuroclear_b200.h for the contract of every symbol.
+#include "../../include/neuroclear_b200.h"
+
+#include "internal.h"
+
+using namespace nc;
+
+static inline cudaStream_t S(nc_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int nc_abi_version(void) { return NC_ABI_VERSION; }
+const char* nc_last_error(void) { return last_error(); }
+
+int nc_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error("no CUDA device");
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_error("no CUDA device");
+  return n;
+}
+
+int64_t nc_dice_geometry(const int32_t size_zyx[3], int32_t roi, int32_t overlap, int32_t padded_zyx[3],
+                         int32_t steps_zyx[3]) {
+  const int step = roi - overlap;
+  if (roi <= 0 || overlap < 0 || step <= 0) return set_error("dice geometry: need 0 <= overlap < roi");
+  int64_t n = 1;
+  for (int i = 0; i < 3; ++i) {
+    if (size_zyx[i] <= 0) return set_error("dice geometry: empty volume");
+    const int counts = (size_zyx[i] + overlap) / step;               // util/util.py:203-205
+    const int pad = step * counts + roi - size_zyx[i];               // util/util.py:207-209
+    padded_zyx[i] = size_zyx[i] + pad;
+    steps_zyx[i] = (padded_zyx[i] - overlap) / step;                 // diceImage_dataset.py:90-92
+    n *= steps_zyx[i];
+  }
+  return n;
+}
+
+int nc_dice_extract_u16(const uint16_t* vol, int32_t vol_z0, int32_t vol_nz, const int32_t size_zyx[3],
+                        const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                        int32_t border, int64_t cube_begin, int32_t cube_count, float* cubes, nc_stream_t stream) {
+  return dice_extract_u16(vol, vol_z0, vol_nz, size_zyx, padded_zyx, steps_zyx, roi, overlap, border, cube_begin,
+                          cube_count, cubes, S(stream));
+}
+
+int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cout) {
+  if (cin == 1) return static_cast<int64_t>(conv_cin1_stats_tiles(nb, d, h, w));
+  return static_cast<int64_t>(conv3d_k3_stats_tiles(nb, d, h, w, cout));
+}
+
+int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d, int32_t h, int32_t wdt, int32_t cout,
+                          float* y_raw, float* stats_partial, nc_stream_t stream) {
+  return conv3d_cin1_k3_fwd(x, w, nb, d, h, wdt, cout, y_raw, stats_partial, S(stream));
+}
+
+int64_t nc_packed_weight_bytes(int32_t cout, int32_t cin, int32_t transposed) {
+  return static_cast<int64_t>(packed_weight_bytes(cout, cin, 27, transposed));
+}
+int nc_pack_weights_conv3d_k3(const float* w, int32_t cout, int32_t cin, void* packed, nc_stream_t stream) {
+  return pack_weights(w, packed, cout, cin, 27, 0, S(stream));
+}
+int nc_pack_weights_convT3d_k2s2(const float* w, int32_t cin, int32_t cout, void* packed, nc_stream_t stream) {
+  return pack_weights(w, packed, cout, cin, 8, 1, S(stream));
+}
+
+int nc_conv3d_k3_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
+                     int32_t cout, float* y_raw, float* stats_partial, nc_stream_t stream) {
+  return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, 0, S(stream));
+}
+// Not part of the public header: lets the hardware probe choose how the shared-memory descriptor's base-offset
+// field is filled for tap-shifted windows (0 = zero, 1 = (addr >> 7) & 7).
+int nc_probe_conv3d_k3_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
+                           const void* packed, int32_t cout, float* y_raw, float* stats_partial, int32_t mode,
+                           nc_stream_t stream) {
+  return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, mode, S(stream));
+}
+
+int nc_convT3d_k2s2_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
+                        const float* bias, int32_t cout, void* y, int32_t y_ld, int32_t y_coff, nc_stream_t stream) {
+  return convT3d_k2s2_fwd(x, nb, d, h, w, cin, packed, bias, cout, y, y_ld, y_coff, S(stream));
+}
+
+int nc_in_stats_finalize(const float* partial, int32_t nb, int64_t rows, int32_t c, int64_t voxels, float eps,
+                         float* mean_rstd, nc_stream_t stream) {
+  return in_stats_finalize(partial, nb, rows, c, voxels, eps, mean_rstd, S(stream));
+}
+
+int nc_in_relu_apply(const float* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t c,
+                     void* y, int32_t y_ld, int32_t y_coff, void* pooled, nc_stream_t stream) {
+  return in_relu_apply(raw, mean_rstd, nb, d, h, w, c, y, y_ld, y_coff, pooled, S(stream));
+}
+
+int nc_head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* hp, int32_t nb, int32_t d,
+                            int32_t h, int32_t w, int32_t c, int32_t crop, float* y, nc_stream_t stream) {
+  return head_1x1_sigmoid_fwd(raw, mean_rstd, hp, nb, d, h, w, c, crop, y, S(stream));
+}
+
+int nc_blend_gather_f32(const float* pieces, const int64_t* piece_off, const int32_t* piece_z0,
+                        const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                        int32_t out_z0, int32_t out_nz, float* out, nc_stream_t stream) {
+  return blend_gather_f32(pieces, reinterpret_cast<const long long*>(piece_off), piece_z0, padded_zyx, steps_zyx, roi,
+                          overlap, out_z0, out_nz, out, S(stream));
+}
+
+int nc_select_init(const uint64_t ranks[4], void* st, nc_stream_t stream) {
+  return select_init(reinterpret_cast<const unsigned long long*>(ranks), st, S(stream));
+}
+int nc_select_histogram(const float* data, int64_t n, int32_t pass, const void* st, uint64_t* hist,
+                        nc_stream_t stream) {
+  return select_histogram(data, n, pass, st, reinterpret_cast<unsigned long long*>(hist), S(stream));
+}
+int nc_select_update(int32_t pass, void* st, uint64_t* hist, nc_stream_t stream) {
+  return select_update(pass, st, reinterpret_cast<unsigned long long*>(hist), S(stream));
+}
+int nc_percentile_lerp(const void* st, double t_lo, double t_hi, double* out64, float* out32, nc_stream_t stream) {
+  return percentile_lerp(st, t_lo, t_hi, out64, out32, S(stream));
+}
+
+int nc_rescale_u16_crop(const float* vol, int32_t vol_z0, const int32_t padded_zyx[3], const int32_t size_zyx[3],
+                        const float* norm3, int32_t z_begin, int32_t z_count, uint16_t* out, nc_stream_t stream) {
+  return rescale_u16_crop(vol, vol_z0, padded_zyx, size_zyx, norm3, z_begin, z_count, out, S(stream));
+}
+
+int nc_mip_fwd(const float* vol, int32_t d, int32_t h, int32_t w, int32_t axis, int32_t start, int32_t depth,
+               float* proj, int32_t* argmax, nc_stream_t stream) {
+  return mip_fwd(vol, d, h, w, axis, start, depth, proj, argmax, S(stream));
+}
+int nc_mip_bwd(const float* gproj, const int32_t* argmax, int32_t d, int32_t h, int32_t w, int32_t axis, float* gvol,
+               nc_stream_t stream) {
+  return mip_bwd(gproj, argmax, d, h, w, axis, gvol, S(stream));
+}
+
+}  // extern "C"

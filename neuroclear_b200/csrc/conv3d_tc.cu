@@ -1,0 +1,529 @@
+// Implicit-GEMM Conv3d (k3 s1 p1) and ConvTranspose3d (k2 s2) for sm_100a on tcgen05 tensor cores.
+//
+// Replaces the torch.nn.Conv3d / ConvTranspose3d calls of Unet_deconv (reference models/networks.py:478-538,
+// layers U2..U12 of SURVEY.md §2c). Design (not a translation of any library kernel):
+//
+//   * activations are bf16 NDHWC; one GEMM row = one voxel, K = taps x Cin walked as (64-channel chunk, tap)
+//   * a CTA owns an output tile of 8(w) x 16(h) x TD(d) voxels = TD accumulators of 128 rows in TMEM
+//   * the input is staged ONCE per (tile, chunk) as TD+KS-1 halo planes of (8+KS-1) x (16+KS-1) voxels, each
+//     voxel one 128-byte row, written by a 5-D TMA box with SWIZZLE_128B (out-of-volume rows arrive as zeros
+//     = the conv's zero padding). Every filter tap is then just a shifted window into those planes: the
+//     UMMA shared-memory descriptor's start address moves by (kh*(8+KS-1)+kw) rows and the plane index by kd,
+//     with the 8-row-group stride set to one halo line. Input traffic drops from 27x to ~2x of the tile.
+//   * weights are pre-packed per (n-tile, chunk, tap) as the exact swizzled shared-memory image and streamed
+//     with 1-D bulk copies through a ring; one weight stage feeds TD MMAs (one per output plane).
+//   * warp roles: 0 = halo-plane TMA producer, 1 = MMA issuer, 2 = TMEM allocator + weight producer,
+//     4..7 = epilogue (TMEM -> registers -> global). Two accumulator sets ping-pong so the epilogue of
+//     tile i overlaps the MMAs of tile i+1. The grid is persistent (<= #SMs CTAs, static tile stride).
+//   * epilogue MODE 0: raw fp32 NDHWC store + per-tile per-channel (sum, sum of squares) partials taken from
+//     the fp32 accumulators (InstanceNorm statistics, reduced deterministically later);
+//     MODE 1: transposed-conv scatter (voxel (2d+a,2h+b,2w+c)), +bias, bf16 store into a channel slice of the
+//     skip-concat buffer.
+#include <cuda_bf16.h>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace nc {
+
+constexpr int TW = 8;   // tile extent in w  (rows inside one 8-row swizzle group)
+constexpr int TH = 16;  // tile extent in h  (number of 8-row groups of a 128-row MMA)
+
+constexpr int pow2_at_least(int v) { return v <= 32 ? 32 : v <= 64 ? 64 : v <= 128 ? 128 : v <= 256 ? 256 : 512; }
+
+template <int KS, int BN, int TD>
+struct ConvCfg {
+  static constexpr int PAD = KS / 2;
+  static constexpr int HALO_W = TW + KS - 1;
+  static constexpr int HALO_H = TH + KS - 1;
+  static constexpr int PLANE_ROWS = HALO_W * HALO_H;
+  static constexpr int PLANE_BOX_BYTES = PLANE_ROWS * 128;
+  static constexpr int PLANE_BYTES = (PLANE_BOX_BYTES + 1023) / 1024 * 1024;
+  static constexpr int PPC = TD + KS - 1;  // halo planes per (tile, chunk)
+  static constexpr int NSLOT = PPC + 2;    // plane ring depth: two planes of look-ahead
+  static constexpr int TAPS = KS * KS * KS;
+  static constexpr int BSTAGE_BYTES = BN * 128;
+  static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4;  // barriers + per-warp stats scratch
+  static constexpr int SMEM_LIMIT = 232448;
+  static constexpr int NBST_FIT = (SMEM_LIMIT - 1024 - AUX_BYTES - NSLOT * PLANE_BYTES) / BSTAGE_BYTES;
+  static constexpr int NBST = NBST_FIT > 8 ? 8 : NBST_FIT;
+  static constexpr int ACC_COLS = TD * BN;
+  static constexpr int TMEM_COLS = pow2_at_least(2 * ACC_COLS);
+  static constexpr int SMEM_BYTES = 1024 + NSLOT * PLANE_BYTES + NBST * BSTAGE_BYTES + AUX_BYTES;
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(NBST >= 2, "weight ring too shallow");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "bad BN");
+};
+
+struct ConvTcArgs {
+  int W, H, D, NB;
+  int chunks;  // Cin / 64
+  int n_tiles;  // GEMM N / BN
+  int tiles_w, tiles_h, tiles_d;
+  int total_tiles;
+  const uint8_t* wpacked;
+  // MODE 0
+  float* out_raw;        // [NB][D][H][W][ldo]
+  float* stats_partial;  // [spatial tile][2][ldo]
+  int ldo;               // total output channels (row pitch of out_raw)
+  // MODE 1
+  __nv_bfloat16* out_bf16;  // [NB][2D][2H][2W][ld1]
+  const float* bias;
+  int ld1, coff1, cout1;
+  int desc_base_mode;  // 0: base_offset field = 0 (absolute-address swizzle); 1: (addr>>7)&7
+};
+
+struct TileCoord {
+  int n_tile, nb, d0, h0, w0, spatial;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcArgs& a, int tile, int td) {
+  TileCoord t;
+  const int per_n = a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
+  t.n_tile = tile / per_n;
+  int r = tile - t.n_tile * per_n;
+  t.spatial = r;
+  const int wt = r % a.tiles_w;
+  r /= a.tiles_w;
+  const int ht = r % a.tiles_h;
+  r /= a.tiles_h;
+  const int dt = r % a.tiles_d;
+  t.nb = r / a.tiles_d;
+  t.w0 = wt * TW;
+  t.h0 = ht * TH;
+  t.d0 = dt * td;
+  return t;
+}
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values: afterwards lane l holds sum_lanes v[l].
+// Recursive halving: 16+8+4+2+1 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = upper ? v[i + off] : v[i];
+      const float send = upper ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int KS, int BN, int TD, int MODE>
+__global__ void __launch_bounds__(256, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs args) {
+  using C = ConvCfg<KS, BN, TD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + C::NSLOT * C::PLANE_BYTES;
+  uint8_t* aux = smB + C::NBST * C::BSTAGE_BYTES;
+  uint64_t* planeFull = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* planeEmpty = planeFull + C::NSLOT;
+  uint64_t* bFull = planeEmpty + C::NSLOT;
+  uint64_t* bEmpty = bFull + C::NBST;
+  uint64_t* accFull = bEmpty + C::NBST;
+  uint64_t* accEmpty = accFull + 2;
+  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(accEmpty + 2);
+  float* statScratch = reinterpret_cast<float*>(aux + 1024);  // [4 warps][2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmapA);
+    for (int i = 0; i < C::NSLOT; ++i) {
+      ptx::mbar_init(&planeFull[i], 1);
+      ptx::mbar_init(&planeEmpty[i], 1);
+    }
+    for (int i = 0; i < C::NBST; ++i) {
+      ptx::mbar_init(&bFull[i], 1);
+      ptx::mbar_init(&bEmpty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&accFull[i], 1);
+      ptx::mbar_init(&accEmpty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<C::TMEM_COLS>(tmemPtr);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmemPtr;
+
+  const int first_tile = blockIdx.x;
+  const int tile_stride = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ halo-plane producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
+        const TileCoord t = decode_tile(args, tile, TD);
+        for (int c = 0; c < args.chunks; ++c) {
+          for (int i = 0; i < C::PPC; ++i) {
+            ptx::mbar_wait(&planeEmpty[slot], ph ^ 1);
+            ptx::mbar_arrive_expect_tx(&planeFull[slot], C::PLANE_BOX_BYTES);
+            ptx::tma_load_5d(smA + slot * C::PLANE_BYTES, &tmapA, &planeFull[slot], c * 64, t.w0 - C::PAD,
+                             t.h0 - C::PAD, t.d0 - C::PAD + i, t.nb);
+            if (++slot == C::NSLOT) {
+              slot = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ weight-stage producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
+        const TileCoord t = decode_tile(args, tile, TD);
+        const uint8_t* wsrc =
+            args.wpacked + static_cast<size_t>(t.n_tile) * args.chunks * C::TAPS * C::BSTAGE_BYTES;
+        const int nst = args.chunks * C::TAPS;
+        for (int s = 0; s < nst; ++s) {
+          ptx::mbar_wait(&bEmpty[st], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&bFull[st], C::BSTAGE_BYTES);
+          ptx::bulk_load(smB + st * C::BSTAGE_BYTES, wsrc + static_cast<size_t>(s) * C::BSTAGE_BYTES,
+                         C::BSTAGE_BYTES, &bFull[st]);
+          if (++st == C::NBST) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN);
+      constexpr uint32_t SBO_A = C::HALO_W * 128;
+      const uint32_t smA_u32 = ptx::smem_u32(smA);
+      const uint32_t smB_u32 = ptx::smem_u32(smB);
+      int pslot = 0;  // ring position of plane 0 of the current (tile, chunk)
+      uint32_t pph = 0;
+      int bst = 0;
+      uint32_t bph = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = static_cast<uint32_t>(it >> 1);
+        ptx::mbar_wait(&accEmpty[buf], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * C::ACC_COLS;
+        for (int c = 0; c < args.chunks; ++c) {
+          int waited = 0;
+          for (int kd = 0; kd < KS; ++kd) {
+            for (; waited <= TD - 1 + kd; ++waited) {
+              int s = pslot + waited;
+              uint32_t p = pph;
+              if (s >= C::NSLOT) {
+                s -= C::NSLOT;
+                p ^= 1;
+              }
+              ptx::mbar_wait(&planeFull[s], p);
+            }
+            ptx::tc_fence_after();
+            for (int khw = 0; khw < KS * KS; ++khw) {
+              const int kh = khw / KS, kw = khw - kh * KS;
+              ptx::mbar_wait(&bFull[bst], bph);
+              ptx::tc_fence_after();
+              const uint32_t b_addr = smB_u32 + bst * C::BSTAGE_BYTES;
+              const uint32_t first = (c == 0 && kd == 0 && khw == 0) ? 0u : 1u;
+#pragma unroll
+              for (int j = 0; j < TD; ++j) {
+                int s = pslot + j + kd;
+                if (s >= C::NSLOT) s -= C::NSLOT;
+                const uint32_t a_addr = smA_u32 + s * C::PLANE_BYTES + (kh * C::HALO_W + kw) * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t aa = a_addr + k * 32;
+                  const uint32_t bb = b_addr + k * 32;
+                  const uint32_t bo_a = args.desc_base_mode ? ((aa >> 7) & 7) : 0;
+                  const uint64_t adesc = ptx::make_desc_k_sw128(aa, SBO_A, bo_a);
+                  const uint64_t bdesc = ptx::make_desc_k_sw128(bb, 1024, 0);
+                  ptx::umma_bf16(acc0 + j * BN, adesc, bdesc, idesc, (k == 0) ? first : 1u);
+                }
+              }
+              ptx::umma_commit(&bEmpty[bst]);
+              if (++bst == C::NBST) {
+                bst = 0;
+                bph ^= 1;
+              }
+            }
+            // planes whose last reader was this kd group go back to the producer
+            if (kd < KS - 1) {
+              int s = pslot + kd;
+              if (s >= C::NSLOT) s -= C::NSLOT;
+              ptx::umma_commit(&planeEmpty[s]);
+            } else {
+              for (int i = KS - 1; i < C::PPC; ++i) {
+                int s = pslot + i;
+                if (s >= C::NSLOT) s -= C::NSLOT;
+                ptx::umma_commit(&planeEmpty[s]);
+              }
+            }
+          }
+          pslot += C::PPC;
+          if (pslot >= C::NSLOT) {
+            pslot -= C::NSLOT;
+            pph ^= 1;
+          }
+        }
+        ptx::umma_commit(&accFull[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;    // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;  // accumulator row = voxel inside the tile plane
+    const int mw = m & 7, mh = m >> 3;
+    int it = 0;
+    for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
+      const TileCoord t = decode_tile(args, tile, TD);
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      ptx::mbar_wait(&accFull[buf], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * C::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      const int w = t.w0 + mw, h = t.h0 + mh;
+      const bool valid_hw = (w < args.W) && (h < args.H);
+
+      float csum[BN / 32], csq[BN / 32];
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) csum[cc] = csq[cc] = 0.f;
+
+#pragma unroll 1
+      for (int j = 0; j < TD; ++j) {
+        const int d = t.d0 + j;
+        if (d >= args.D) break;  // warp-uniform
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t raw[32];
+          ptx::tmem_ld32(acc0 + j * BN + cc * 32, raw);
+          ptx::tmem_ld_wait();
+          if constexpr (MODE == 0) {
+            const int co = t.n_tile * BN + cc * 32;
+            if (valid_hw) {
+              float4* dst = reinterpret_cast<float4*>(
+                  args.out_raw + (((static_cast<size_t>(t.nb) * args.D + d) * args.H + h) * args.W + w) * args.ldo +
+                  co);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                                     __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+            }
+            float v[32], v2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = valid_hw ? __uint_as_float(raw[i]) : 0.f;
+              v[i] = x;
+              v2[i] = x * x;
+            }
+            csum[cc] += warp_colsum32(v, lane);
+            csq[cc] += warp_colsum32(v2, lane);
+          } else {
+            const int n0 = t.n_tile * BN + cc * 32;
+            const int tap = n0 / args.cout1;
+            const int co = n0 - tap * args.cout1;
+            if (valid_hw) {
+              const int od = 2 * d + (tap >> 2), oh = 2 * h + ((tap >> 1) & 1), ow = 2 * w + (tap & 1);
+              __nv_bfloat16* dst =
+                  args.out_bf16 +
+                  (((static_cast<size_t>(t.nb) * (2 * args.D) + od) * (2 * args.H) + oh) * (2 * args.W) + ow) *
+                      args.ld1 +
+                  args.coff1 + co;
+              const float* bp = args.bias + co;
+              uint4* dst4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float lo = __uint_as_float(raw[8 * i + 2 * e]) + __ldg(bp + 8 * i + 2 * e);
+                  const float hi = __uint_as_float(raw[8 * i + 2 * e + 1]) + __ldg(bp + 8 * i + 2 * e + 1);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                dst4[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      }
+      // accumulators are drained: hand the TMEM set back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&accEmpty[buf]);
+
+      if constexpr (MODE == 0) {
+        // lane l of warp q holds the column-l sums of its 32 rows; combine the 4 warps in fixed order
+        float* mine = statScratch + q * 2 * BN;
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          mine[cc * 32 + lane] = csum[cc];
+          mine[BN + cc * 32 + lane] = csq[cc];
+        }
+        ptx::named_bar_sync(1, 128);
+        const int e = threadIdx.x - 128;  // 0..127
+        for (int i = e; i < 2 * BN; i += 128) {
+          const float s = (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
+          const int which = i / BN, col = i - which * BN;
+          args.stats_partial[(static_cast<size_t>(t.spatial) * 2 + which) * args.ldo + t.n_tile * BN + col] = s;
+        }
+        ptx::named_bar_sync(1, 128);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+// Packed image: [n_tile][chunk][tap][row r < BN][128 B], 16-byte unit j of row r stored at unit j ^ (r & 7).
+// conv:  w is OIDHW fp32 (Cout, Cin, k, k, k); GEMM column n = output channel.
+// convT: w is IODHW fp32 (Cin, Cout, 2, 2, 2); GEMM column n = tap * Cout + co with tap = (a*2+b)*2+c.
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                    int taps, int BN, int transposed) {
+  const int chunks = Cin / 64;
+  const int ngemm = transposed ? 8 * Cout : Cout;
+  const int gtaps = transposed ? 1 : taps;
+  const size_t total = static_cast<size_t>(ngemm) * Cin * gtaps;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = idx % 64;
+    size_t r0 = idx / 64;
+    const int r = r0 % BN;
+    r0 /= BN;
+    const int tap = r0 % gtaps;
+    r0 /= gtaps;
+    const int chunk = r0 % chunks;
+    const int n_tile = r0 / chunks;
+    const int n = n_tile * BN + r;
+    const int ci = chunk * 64 + k;
+    float v;
+    if (!transposed) {
+      v = w[(static_cast<size_t>(n) * Cin + ci) * taps + tap];
+    } else {
+      const int t8 = n / Cout, co = n - t8 * Cout;
+      v = w[(static_cast<size_t>(ci) * Cout + co) * 8 + t8];
+    }
+    const size_t stage = (static_cast<size_t>(n_tile) * chunks + chunk) * gtaps + tap;
+    const size_t off = stage * BN * 64 + static_cast<size_t>(r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
+    out[off] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int D, int NB, int boxW, int boxH) {
+  auto encode = get_tensor_map_encoder();
+  if (!encode) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)NB};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)boxW, (cuuint32_t)boxH, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <int KS, int BN, int TD, int MODE>
+static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
+  using C = ConvCfg<KS, BN, TD>;
+  CUtensorMap tm;
+  if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H)) return rc;
+  a.tiles_w = (a.W + TW - 1) / TW;
+  a.tiles_h = (a.H + TH - 1) / TH;
+  a.tiles_d = (a.D + TD - 1) / TD;
+  a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
+  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, a);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv3d_k3_bn(int Cout) { return Cout == 64 ? 64 : 128; }
+int conv3d_k3_td(int Cout) { return Cout == 64 ? 3 : 2; }
+
+size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout) {
+  const int td = conv3d_k3_td(Cout);
+  return static_cast<size_t>(NB) * ((D + td - 1) / td) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+}
+
+int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, float* y_raw,
+                  float* stats_partial, int desc_base_mode, cudaStream_t stream) {
+  if (Cin % 64 || Cout % 64) return set_error("conv3d_k3_fwd: Cin and Cout must be multiples of 64");
+  ConvTcArgs a{};
+  a.W = W, a.H = H, a.D = D, a.NB = NB;
+  a.chunks = Cin / 64;
+  a.wpacked = static_cast<const uint8_t*>(wpacked);
+  a.out_raw = y_raw;
+  a.stats_partial = stats_partial;
+  a.ldo = Cout;
+  a.desc_base_mode = desc_base_mode;
+  if (Cout == 64) {
+    a.n_tiles = 1;
+    return launch_cfg<3, 64, 3, 0>(x, a, Cin, stream);
+  }
+  if (Cout % 128) return set_error("conv3d_k3_fwd: Cout must be 64 or a multiple of 128");
+  a.n_tiles = Cout / 128;
+  return launch_cfg<3, 128, 2, 0>(x, a, Cin, stream);
+}
+
+int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, const float* bias,
+                     int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream) {
+  if (Cin % 64 || (8 * Cout) % 128 || Cout % 32) return set_error("convT3d_k2s2_fwd: unsupported channel counts");
+  if (y_ld % 8 || y_coff % 8) return set_error("convT3d_k2s2_fwd: output slice must be 16-byte aligned");
+  ConvTcArgs a{};
+  a.W = W, a.H = H, a.D = D, a.NB = NB;
+  a.chunks = Cin / 64;
+  a.wpacked = static_cast<const uint8_t*>(wpacked);
+  a.out_bf16 = static_cast<__nv_bfloat16*>(y);
+  a.bias = bias;
+  a.ld1 = y_ld, a.coff1 = y_coff, a.cout1 = Cout;
+  a.n_tiles = 8 * Cout / 128;
+  return launch_cfg<1, 128, 2, 1>(x, a, Cin, stream);
+}
+
+size_t packed_weight_bytes(int Cout, int Cin, int taps, int transposed) {
+  return static_cast<size_t>(transposed ? 8 * Cout : Cout) * Cin * (transposed ? 1 : taps) * 2;
+}
+
+int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int transposed, cudaStream_t stream) {
+  if (Cin % 64) return set_error("pack_weights: Cin must be a multiple of 64");
+  const int BN = transposed ? 128 : conv3d_k3_bn(Cout);
+  const int ngemm = transposed ? 8 * Cout : Cout;
+  if (ngemm % BN) return set_error("pack_weights: GEMM N not a multiple of the N tile");
+  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), Cout, Cin, taps, BN,
+                                                         transposed);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace nc

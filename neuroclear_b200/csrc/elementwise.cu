@@ -1,0 +1,654 @@
+// Memory-bound kernels of the hot path: dice extraction, first-layer direct conv, InstanceNorm
+// finalize/apply(+pool), the 1x1x1+sigmoid head, overlap blend, radix-select percentile, rescale/cast/crop and
+// the max-intensity projection.  All are coalesced, vectorised where the layout allows, and bit-exact where the
+// reference is integer / fixed-order fp32 arithmetic.  Reference citations are in include/neuroclear_b200.h.
+#include <cuda_bf16.h>
+
+#include "internal.h"
+
+namespace nc {
+
+// ------------------------------------------------------------------------------------------------ dice
+__device__ __forceinline__ int reflect_index(int j, int n) {
+  // numpy 'reflect' (no edge repeat): -i -> i, n-1+i -> n-1-i
+  if (j < 0) j = -j;
+  if (j >= n) j = 2 * (n - 1) - j;
+  return j;
+}
+
+__global__ void dice_extract_kernel(const uint16_t* __restrict__ vol, int vz0, int vnz, int Z, int Y, int X, int Pz,
+                                    int Py, int Px, int ny, int nx, int step, int bc, int E, long long cube_begin,
+                                    float* __restrict__ out) {
+  const int local_cube = blockIdx.y;
+  const long long cube = cube_begin + local_cube;
+  const int cx = static_cast<int>(cube % nx);
+  const int cy = static_cast<int>((cube / nx) % ny);
+  const int cz = static_cast<int>(cube / (static_cast<long long>(nx) * ny));
+  const unsigned E3 = static_cast<unsigned>(E) * E * E;
+  float* dst = out + static_cast<size_t>(local_cube) * E3;
+  for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < E3; r += gridDim.x * blockDim.x) {
+    const int c = r % E;
+    const unsigned r2 = r / E;
+    const int b = r2 % E;
+    const int a = r2 / E;
+    const int z = reflect_index(cz * step - bc + a, Pz);
+    const int y = reflect_index(cy * step - bc + b, Py);
+    const int x = reflect_index(cx * step - bc + c, Px);
+    float v = 0.f;  // far-end zero padding of pad_for_dicing
+    if (z < Z && y < Y && x < X) {
+      const int zl = z - vz0;
+      if (zl >= 0 && zl < vnz) v = static_cast<float>(vol[(static_cast<size_t>(zl) * Y + y) * X + x]);
+    }
+    dst[r] = __fdiv_rn(v, 65535.0f);
+  }
+}
+
+int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
+                     int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
+                     cudaStream_t stream) {
+  if (cube_count <= 0) return 0;
+  if (cube_count > 65535) return set_error("dice_extract: at most 65535 cubes per call");
+  const int E = roi + 2 * border;
+  if (border >= padded[0] || border >= padded[1] || border >= padded[2])
+    return set_error("dice_extract: border_cut must be smaller than the padded volume");
+  const unsigned E3 = static_cast<unsigned>(E) * E * E;
+  dim3 grid((E3 + 255) / 256, cube_count);
+  if (grid.x > 4096) grid.x = 4096;
+  dice_extract_kernel<<<grid, 256, 0, stream>>>(vol, vz0, vnz, size[0], size[1], size[2], padded[0], padded[1],
+                                                padded[2], steps[1], steps[2], roi - overlap, border, E, cube_begin,
+                                                cubes);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ first layer
+constexpr int C1_TW = 28, C1_TH = 8, C1_WSTEP = 4;
+
+__global__ void __launch_bounds__(256)
+conv_cin1_k3_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int D, int H, int W, int tiles_w,
+                    int tiles_h, float* __restrict__ y_raw, float* __restrict__ stats_partial) {
+  __shared__ float halo[3][C1_TH + 2][C1_TW + 4];
+  __shared__ float red[8][2][64];
+  const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
+  const int d = blockIdx.y, nb = blockIdx.z;
+  const int w0 = tw * C1_TW, h0 = th * C1_TH;
+  const float* xin = x + static_cast<size_t>(nb) * D * H * W;
+  for (int i = threadIdx.x; i < 3 * (C1_TH + 2) * (C1_TW + 2); i += 256) {
+    const int ww = i % (C1_TW + 2);
+    const int hh = (i / (C1_TW + 2)) % (C1_TH + 2);
+    const int dd = i / ((C1_TW + 2) * (C1_TH + 2));
+    const int gz = d - 1 + dd, gy = h0 - 1 + hh, gx = w0 - 1 + ww;
+    float v = 0.f;
+    if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) v = xin[(static_cast<size_t>(gz) * H + gy) * W + gx];
+    halo[dd][hh][ww] = v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float w0r[27], w1r[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    w0r[t] = __ldg(wgt + (2 * lane) * 27 + t);
+    w1r[t] = __ldg(wgt + (2 * lane + 1) * 27 + t);
+  }
+  __syncthreads();
+  const int h = h0 + warp;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (h < H) {
+#pragma unroll 1
+    for (int s = 0; s < C1_TW / C1_WSTEP; ++s) {
+      float acc0[C1_WSTEP], acc1[C1_WSTEP];
+#pragma unroll
+      for (int v = 0; v < C1_WSTEP; ++v) acc0[v] = acc1[v] = 0.f;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          float in[C1_WSTEP + 2];
+#pragma unroll
+          for (int i = 0; i < C1_WSTEP + 2; ++i) in[i] = halo[kd][warp + kh][s * C1_WSTEP + i];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int v = 0; v < C1_WSTEP; ++v) {
+              acc0[v] = fmaf(in[v + kw], w0r[(kd * 3 + kh) * 3 + kw], acc0[v]);
+              acc1[v] = fmaf(in[v + kw], w1r[(kd * 3 + kh) * 3 + kw], acc1[v]);
+            }
+        }
+#pragma unroll
+      for (int v = 0; v < C1_WSTEP; ++v) {
+        const int w = w0 + s * C1_WSTEP + v;
+        if (w < W) {
+          float2* dst = reinterpret_cast<float2*>(
+              y_raw + ((((static_cast<size_t>(nb) * D + d) * H + h) * W + w) * 64 + 2 * lane));
+          *dst = make_float2(acc0[v], acc1[v]);
+          s0 += acc0[v];
+          s1 += acc1[v];
+          q0 = fmaf(acc0[v], acc0[v], q0);
+          q1 = fmaf(acc1[v], acc1[v], q1);
+        }
+      }
+    }
+  }
+  red[warp][0][2 * lane] = s0;
+  red[warp][0][2 * lane + 1] = s1;
+  red[warp][1][2 * lane] = q0;
+  red[warp][1][2 * lane + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][which][c];
+    const size_t row = (static_cast<size_t>(nb) * D + d) * gridDim.x + blockIdx.x;
+    stats_partial[(row * 2 + which) * 64 + c] = t;
+  }
+}
+
+size_t conv_cin1_stats_tiles(int NB, int D, int H, int W) {
+  return static_cast<size_t>(NB) * D * ((H + C1_TH - 1) / C1_TH) * ((W + C1_TW - 1) / C1_TW);
+}
+
+int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, float* y_raw,
+                       float* stats_partial, cudaStream_t stream) {
+  if (Cout != 64) return set_error("conv3d_cin1_k3_fwd: Cout must be 64");
+  if (D > 65535 || NB > 65535) return set_error("conv3d_cin1_k3_fwd: D / NB too large");
+  const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH;
+  dim3 grid(tiles_w * tiles_h, D, NB);
+  conv_cin1_k3_kernel<<<grid, 256, 0, stream>>>(x, w, D, H, W, tiles_w, tiles_h, y_raw, stats_partial);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ InstanceNorm
+__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int C, double inv_n,
+                                         float eps, float* __restrict__ mean_rstd) {
+  __shared__ double ssum[8][32], ssq[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int nb = blockIdx.y;
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const float* p = partial + static_cast<size_t>(nb) * rows * 2 * C;
+    for (long long r = threadIdx.y; r < rows; r += 8) {
+      s += static_cast<double>(p[(r * 2) * C + c]);
+      q += static_cast<double>(p[(r * 2 + 1) * C + c]);
+    }
+  }
+  ssum[threadIdx.y][threadIdx.x] = s;
+  ssq[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double S = 0.0, Q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      S += ssum[i][threadIdx.x];
+      Q += ssq[i][threadIdx.x];
+    }
+    const double mean = S * inv_n;
+    double var = Q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[(static_cast<size_t>(nb) * 2) * C + c] = static_cast<float>(mean);
+    mean_rstd[(static_cast<size_t>(nb) * 2 + 1) * C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps,
+                      float* mean_rstd, cudaStream_t stream) {
+  dim3 grid((C + 31) / 32, NB), block(32, 8);
+  in_stats_finalize_kernel<<<grid, block, 0, stream>>>(partial, rows, C, 1.0 / static_cast<double>(voxels), eps,
+                                                       mean_rstd);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// eight channels of one voxel: relu((x-mean)*rstd)
+__device__ __forceinline__ void norm8(const float* __restrict__ src, const float (&mu)[8], const float (&rs)[8],
+                                      float (&o)[8]) {
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaxf((x[i] - mu[i]) * rs[i], 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+in_relu_apply_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, long long voxels, int C,
+                     __nv_bfloat16* __restrict__ y, int y_ld, int y_coff) {
+  const int nb = blockIdx.y;
+  const int cg_per = C / 8;
+  const long long total = voxels * cg_per;
+  const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+    const long long vox = idx / cg_per;
+    const int cg = static_cast<int>(idx - vox * cg_per);
+    float mu[8], rs[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = __ldg(mr + cg * 8 + i);
+      rs[i] = __ldg(mr + C + cg * 8 + i);
+    }
+    const long long gv = static_cast<long long>(nb) * voxels + vox;
+    norm8(raw + gv * C + cg * 8, mu, rs, o);
+    uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                          pack_bf16x2(o[6], o[7]));
+    *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+in_relu_pool_apply_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
+                          int C, __nv_bfloat16* __restrict__ y, int y_ld, int y_coff,
+                          __nv_bfloat16* __restrict__ pooled) {
+  const int nb = blockIdx.y;
+  const int cg_per = C / 8;
+  const int PD = D / 2, PH = H / 2, PW = W / 2;
+  const long long total = static_cast<long long>(PD) * PH * PW * cg_per;
+  const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+    const int cg = static_cast<int>(idx % cg_per);
+    long long r = idx / cg_per;
+    const int pw = static_cast<int>(r % PW);
+    r /= PW;
+    const int ph = static_cast<int>(r % PH);
+    const int pd = static_cast<int>(r / PH);
+    float mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = __ldg(mr + cg * 8 + i);
+      rs[i] = __ldg(mr + C + cg * 8 + i);
+    }
+    float mx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx[i] = 0.f;  // post-ReLU values are >= 0
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int dz = 2 * pd + (k >> 2), hy = 2 * ph + ((k >> 1) & 1), wx = 2 * pw + (k & 1);
+      const long long gv = ((static_cast<long long>(nb) * D + dz) * H + hy) * W + wx;
+      float o[8];
+      norm8(raw + gv * C + cg * 8, mu, rs, o);
+      uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                            pack_bf16x2(o[6], o[7]));
+      *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], o[i]);
+    }
+    const long long pv = ((static_cast<long long>(nb) * PD + pd) * PH + ph) * PW + pw;
+    uint4 pk = make_uint4(pack_bf16x2(mx[0], mx[1]), pack_bf16x2(mx[2], mx[3]), pack_bf16x2(mx[4], mx[5]),
+                          pack_bf16x2(mx[6], mx[7]));
+    *reinterpret_cast<uint4*>(pooled + pv * C + cg * 8) = pk;
+  }
+}
+
+int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
+                  int y_coff, void* pooled, cudaStream_t stream) {
+  if (C % 8 || y_ld % 8 || y_coff % 8) return set_error("in_relu_apply: channel counts must be multiples of 8");
+  if (NB > 65535) return set_error("in_relu_apply: NB too large");
+  const int blocks = num_sms() * 8;
+  if (pooled) {
+    if ((D | H | W) & 1) return set_error("in_relu_apply: pooling needs even D, H, W");
+    in_relu_pool_apply_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, D, H, W, C,
+                                                                    static_cast<__nv_bfloat16*>(y), y_ld, y_coff,
+                                                                    static_cast<__nv_bfloat16*>(pooled));
+  } else {
+    in_relu_apply_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, static_cast<long long>(D) * H * W, C,
+                                                               static_cast<__nv_bfloat16*>(y), y_ld, y_coff);
+  }
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ head
+// 8 lanes per voxel, 8 channels per lane (C == 64): IN + ReLU + dot(w1) + b1, * w2 + b2, sigmoid.
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, const float* __restrict__ hp, int D,
+            int H, int W, int crop, float* __restrict__ y) {
+  constexpr int C = 64;
+  const int nb = blockIdx.y;
+  const int sub = threadIdx.x & 7;
+  const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
+  float mu[8], rs[8], w1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = __ldg(mr + sub * 8 + i);
+    rs[i] = __ldg(mr + C + sub * 8 + i);
+    w1[i] = __ldg(hp + sub * 8 + i);
+  }
+  const float b1 = __ldg(hp + C), w2 = __ldg(hp + C + 1), b2 = __ldg(hp + C + 2);
+  const long long voxels = static_cast<long long>(D) * H * W;
+  const int OD = D - 2 * crop, OH = H - 2 * crop, OW = W - 2 * crop;
+  // a warp handles 4 consecutive voxels per step; the loop bound is warp-uniform so the shuffles are safe
+  const long long warps_total = static_cast<long long>(gridDim.x) * 8;
+  for (long long q = blockIdx.x * 8ll + (threadIdx.x >> 5); q * 4 < voxels; q += warps_total) {
+    const long long vox = q * 4 + ((threadIdx.x & 31) >> 3);
+    const bool ok = vox < voxels;
+    const long long gv = static_cast<long long>(nb) * voxels + (ok ? vox : 0);
+    float o[8];
+    norm8(raw + gv * C + sub * 8, mu, rs, o);
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t = fmaf(o[i], w1[i], t);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    if (sub == 0 && ok) {
+      const int w = static_cast<int>(vox % W);
+      const long long r = vox / W;
+      const int h = static_cast<int>(r % H);
+      const int d = static_cast<int>(r / H);
+      const int od = d - crop, oh = h - crop, ow = w - crop;
+      if (od >= 0 && od < OD && oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
+        const float u = fmaf(w2, t + b1, b2);
+        y[((static_cast<long long>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-u));
+      }
+    }
+  }
+}
+
+int head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* hp, int NB, int D, int H, int W,
+                         int C, int crop, float* y, cudaStream_t stream) {
+  if (C != 64) return set_error("head_1x1_sigmoid_fwd: C must be 64");
+  if (crop < 0 || 2 * crop >= D || 2 * crop >= H || 2 * crop >= W) return set_error("head: bad crop");
+  const int blocks = num_sms() * 8;
+  head_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, hp, D, H, W, crop, y);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ blend
+struct AxisCover {
+  int j0, j1;  // lower covering cube (or -1) and upper covering cube
+};
+__device__ __forceinline__ AxisCover axis_cover(int q, int step, int roi, int k) {
+  AxisCover c;
+  c.j1 = min(q / step, k - 1);
+  c.j0 = (c.j1 >= 1 && q < (c.j1 - 1) * step + roi) ? c.j1 - 1 : -1;
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+blend_gather_kernel(const float* __restrict__ pieces, const long long* __restrict__ piece_off,
+                    const int* __restrict__ piece_z0, int Py, int Px, int nz, int ny, int nx, int roi, int step,
+                    int out_z0, float* __restrict__ out) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= Px) return;
+  const int y = blockIdx.y;
+  const int z = out_z0 + blockIdx.z;
+  const AxisCover cz = axis_cover(z, step, roi, nz), cy = axis_cover(y, step, roi, ny),
+                  cx = axis_cover(x, step, roi, nx);
+  float acc = 0.f;
+  int n = 0;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int jz = a ? cz.j1 : cz.j0;
+    if (jz < 0) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int jy = b ? cy.j1 : cy.j0;
+      if (jy < 0) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int jx = c ? cx.j1 : cx.j0;
+        if (jx < 0) continue;
+        const long long cube = (static_cast<long long>(jz) * ny + jy) * nx + jx;
+        const long long off = piece_off[cube];
+        const int lz = z - jz * step - piece_z0[cube];
+        const float v = pieces[off + (static_cast<long long>(lz) * roi + (y - jy * step)) * roi + (x - jx * step)];
+        acc = acc + v * 0.125f;  // visual_ret += cube / 8 (assemble_dice.py:172), ascending cube index
+        ++n;
+      }
+    }
+  }
+  // (visual_ret / mask_ret) * 8  (assemble_dice.py:184)
+  out[(static_cast<size_t>(blockIdx.z) * Py + y) * Px + x] = __fdiv_rn(acc, static_cast<float>(n)) * 8.0f;
+}
+
+int blend_gather_f32(const float* pieces, const long long* piece_off, const int* piece_z0, const int* padded,
+                     const int* steps, int roi, int overlap, int out_z0, int out_nz, float* out,
+                     cudaStream_t stream) {
+  if (overlap <= 0) return set_error("blend_gather: overlap must be > 0 (the reference produces zeros otherwise)");
+  if (2 * overlap > roi) return set_error("blend_gather: overlap must be <= roi - overlap");
+  if (out_nz <= 0) return 0;
+  if (out_nz > 65535 || padded[1] > 65535) return set_error("blend_gather: slab too large for one launch");
+  dim3 grid((padded[2] + 255) / 256, padded[1], out_nz);
+  blend_gather_kernel<<<grid, 256, 0, stream>>>(pieces, piece_off, piece_z0, padded[1], padded[2], steps[0], steps[1],
+                                                steps[2], roi, roi - overlap, out_z0, out);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ radix select
+struct SelectState {
+  unsigned long long rank[4];
+  unsigned int prefix[4];
+};
+constexpr int SEL_BINS = 4096;
+__host__ __device__ inline int sel_shift(int pass) { return pass == 0 ? 20 : pass == 1 ? 8 : 0; }
+__host__ __device__ inline int sel_bits(int pass) { return pass == 2 ? 8 : 12; }
+
+__global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsigned long long r1,
+                                   unsigned long long r2, unsigned long long r3) {
+  st->rank[0] = r0, st->rank[1] = r1, st->rank[2] = r2, st->rank[3] = r3;
+  for (int i = 0; i < 4; ++i) st->prefix[i] = 0;
+}
+
+__global__ void __launch_bounds__(512)
+select_hist_kernel(const float* __restrict__ data, long long n, int pass, const SelectState* __restrict__ st,
+                   unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int sh[];  // [ntab][bins]
+  const int shift = sel_shift(pass), bits = sel_bits(pass);
+  const int bins = 1 << bits;
+  const int ntab = pass == 0 ? 1 : 4;
+  for (int i = threadIdx.x; i < ntab * bins; i += blockDim.x) sh[i] = 0;
+  unsigned int pre[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) pre[t] = st->prefix[t];
+  const unsigned int hi_mask = pass == 0 ? 0u : ~((1u << (shift + bits)) - 1u);
+  __syncthreads();
+  const long long n4 = n >> 2;
+  const float4* d4 = reinterpret_cast<const float4*>(data);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldcs(d4 + i);
+    const unsigned int u[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned int digit = (u[e] >> shift) & (bins - 1);
+      if (pass == 0) {
+        atomicAdd(&sh[digit], 1u);
+      } else {
+        const unsigned int hi = u[e] & hi_mask;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (hi == pre[t]) atomicAdd(&sh[t * bins + digit], 1u);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // scalar tail
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int u = __float_as_uint(data[i]);
+      const unsigned int digit = (u >> shift) & (bins - 1);
+      if (pass == 0) {
+        atomicAdd(&sh[digit], 1u);
+      } else {
+        const unsigned int hi = u & hi_mask;
+        for (int t = 0; t < 4; ++t)
+          if (hi == pre[t]) atomicAdd(&sh[t * bins + digit], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntab * bins; i += blockDim.x) {
+    const unsigned int c = sh[i];
+    if (c) atomicAdd(&hist[(i / bins) * SEL_BINS + (i % bins)], static_cast<unsigned long long>(c));
+  }
+}
+
+__global__ void select_update_kernel(int pass, SelectState* st, unsigned long long* hist) {
+  const int shift = sel_shift(pass), bins = 1 << sel_bits(pass);
+  if (threadIdx.x < 4) {
+    const int t = threadIdx.x;
+    const unsigned long long* h = hist + (pass == 0 ? 0 : t) * SEL_BINS;
+    unsigned long long cum = 0, rank = st->rank[t];
+    int b = 0;
+    for (; b < bins - 1; ++b) {
+      if (cum + h[b] > rank) break;
+      cum += h[b];
+    }
+    st->rank[t] = rank - cum;
+    st->prefix[t] |= static_cast<unsigned int>(b) << shift;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * SEL_BINS; i += blockDim.x) hist[i] = 0;
+}
+
+// numpy _lerp on float32 order statistics with float64 gamma (numpy/lib/_function_base_impl.py):
+//   diff = f32(b - a);  r = a + diff*t;  if t >= 0.5: r = b - diff*(1-t)      (r, t in float64)
+__device__ inline double np_lerp(float a, float b, double t) {
+  const float diff = __fsub_rn(b, a);
+  double r = static_cast<double>(a) + static_cast<double>(diff) * t;
+  if (t >= 0.5) r = static_cast<double>(b) - static_cast<double>(diff) * (1.0 - t);
+  return r;
+}
+__global__ void percentile_lerp_kernel(const SelectState* st, double t_lo, double t_hi, double* out64, float* out32) {
+  const double p_lo = np_lerp(__uint_as_float(st->prefix[0]), __uint_as_float(st->prefix[1]), t_lo);
+  const double p_hi = np_lerp(__uint_as_float(st->prefix[2]), __uint_as_float(st->prefix[3]), t_hi);
+  out64[0] = p_lo;
+  out64[1] = p_hi;
+  out32[0] = static_cast<float>(p_lo);
+  out32[1] = static_cast<float>(p_hi);
+  out32[2] = static_cast<float>(p_hi - p_lo);
+}
+
+int select_init(const unsigned long long* ranks, void* st, cudaStream_t stream) {
+  select_init_kernel<<<1, 1, 0, stream>>>(static_cast<SelectState*>(st), ranks[0], ranks[1], ranks[2], ranks[3]);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+int select_histogram(const float* data, long long n, int pass, const void* st, unsigned long long* hist,
+                     cudaStream_t stream) {
+  if (pass < 0 || pass > 2) return set_error("select_histogram: pass must be 0, 1 or 2");
+  if (reinterpret_cast<uintptr_t>(data) & 15) return set_error("select_histogram: data must be 16-byte aligned");
+  const int ntab = pass == 0 ? 1 : 4;
+  const size_t smem = static_cast<size_t>(ntab) * (1 << sel_bits(pass)) * sizeof(unsigned int);
+  static bool attr = false;
+  if (!attr) {
+    NC_CUDA(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SEL_BINS * 4));
+    attr = true;
+  }
+  select_hist_kernel<<<num_sms() * 2, 512, smem, stream>>>(data, n, pass, static_cast<const SelectState*>(st), hist);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+int select_update(int pass, void* st, unsigned long long* hist, cudaStream_t stream) {
+  if (pass < 0 || pass > 2) return set_error("select_update: pass must be 0, 1 or 2");
+  select_update_kernel<<<1, 256, 0, stream>>>(pass, static_cast<SelectState*>(st), hist);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+int percentile_lerp(const void* st, double t_lo, double t_hi, double* out64, float* out32, cudaStream_t stream) {
+  percentile_lerp_kernel<<<1, 1, 0, stream>>>(static_cast<const SelectState*>(st), t_lo, t_hi, out64, out32);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ rescale
+__global__ void __launch_bounds__(256)
+rescale_u16_crop_kernel(const float* __restrict__ vol, int vol_z0, int Py, int Px, int Y, int X,
+                        const float* __restrict__ norm3, int z_begin, uint16_t* __restrict__ out) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= X) return;
+  const int y = blockIdx.y;
+  const int z = z_begin + blockIdx.z;
+  float v = __ldcs(vol + (static_cast<size_t>(z - vol_z0) * Py + y) * Px + x);
+  if (norm3) {
+    const float lo = norm3[0], hi = norm3[1], span = norm3[2];
+    if (span != 0.f) {
+      v = fminf(fmaxf(v, lo), hi);              // np.clip(image, imin, imax)
+      v = __fdiv_rn(__fsub_rn(v, lo), span);    // (image - imin) / (imax - imin)
+    } else {
+      v = fminf(fmaxf(v, 0.f), 1.f);
+    }
+  }
+  v = __fmul_rn(v, 65535.0f);                   // *= 2**16 - 1
+  out[(static_cast<size_t>(blockIdx.z) * Y + y) * X + x] = static_cast<uint16_t>(static_cast<int>(v));  // truncation
+}
+
+int rescale_u16_crop(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3,
+                     int z_begin, int z_count, uint16_t* out, cudaStream_t stream) {
+  if (z_count <= 0) return 0;
+  if (z_count > 65535 || size[1] > 65535) return set_error("rescale_u16_crop: slab too large for one launch");
+  if (z_begin < vol_z0 || z_begin + z_count > size[0]) return set_error("rescale_u16_crop: plane range out of bounds");
+  dim3 grid((size[2] + 255) / 256, size[1], z_count);
+  rescale_u16_crop_kernel<<<grid, 256, 0, stream>>>(vol, vol_z0, padded[1], padded[2], size[1], size[2], norm3,
+                                                    z_begin, out);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ MIP
+__global__ void mip_fwd_kernel(const float* __restrict__ vol, int D, int H, int W, int axis, int start, int depth,
+                               float* __restrict__ proj, int* __restrict__ argmax) {
+  const int n0 = axis == 0 ? H : D, n1 = axis == 2 ? H : W;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n0 * n1) return;
+  const int i = idx / n1, j = idx - i * n1;
+  size_t base, stride;
+  if (axis == 0) {
+    base = static_cast<size_t>(i) * W + j, stride = static_cast<size_t>(H) * W;
+  } else if (axis == 1) {
+    base = static_cast<size_t>(i) * H * W + j, stride = W;
+  } else {
+    base = (static_cast<size_t>(i) * H + j) * W, stride = 1;
+  }
+  float best = vol[base + start * stride];
+  int arg = start;
+  for (int k = 1; k < depth; ++k) {
+    const float v = vol[base + (start + k) * stride];
+    if (v > best) {  // first maximal index wins, as torch.max(dim)
+      best = v;
+      arg = start + k;
+    }
+  }
+  proj[idx] = best;
+  if (argmax) argmax[idx] = arg;
+}
+
+__global__ void mip_bwd_kernel(const float* __restrict__ gproj, const int* __restrict__ argmax, int D, int H, int W,
+                               int axis, float* __restrict__ gvol) {
+  const int n0 = axis == 0 ? H : D, n1 = axis == 2 ? H : W;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n0 * n1) return;
+  const int i = idx / n1, j = idx - i * n1;
+  const int k = argmax[idx];
+  size_t off;
+  if (axis == 0)
+    off = (static_cast<size_t>(k) * H + i) * W + j;
+  else if (axis == 1)
+    off = (static_cast<size_t>(i) * H + k) * W + j;
+  else
+    off = (static_cast<size_t>(i) * H + j) * W + k;
+  gvol[off] += gproj[idx];
+}
+
+int mip_fwd(const float* vol, int D, int H, int W, int axis, int start, int depth, float* proj, int* argmax,
+            cudaStream_t stream) {
+  if (axis < 0 || axis > 2) return set_error("mip: axis must be 0, 1 or 2");
+  const int len = axis == 0 ? D : axis == 1 ? H : W;
+  if (depth < 1 || start < 0 || start + depth > len) return set_error("mip: slab [start, start+depth) out of range");
+  const int n = (axis == 0 ? H : D) * (axis == 2 ? H : W);
+  mip_fwd_kernel<<<(n + 255) / 256, 256, 0, stream>>>(vol, D, H, W, axis, start, depth, proj, argmax);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+int mip_bwd(const float* gproj, const int* argmax, int D, int H, int W, int axis, float* gvol, cudaStream_t stream) {
+  if (axis < 0 || axis > 2) return set_error("mip: axis must be 0, 1 or 2");
+  const int n = (axis == 0 ? H : D) * (axis == 2 ? H : W);
+  mip_bwd_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gproj, argmax, D, H, W, axis, gvol);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace nc

@@ -1,0 +1,69 @@
+// Internal (non-ABI) declarations shared by the translation units of libneuroclear_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace nc {
+
+// Thread-local last-error string behind nc_last_error(); returns -1 so callers can `return set_error(...)`.
+int set_error(const char* fmt, ...);
+
+#define NC_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) return ::nc::set_error("%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+int num_sms();
+
+using TensorMapEncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                            CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                            CUtensorMapFloatOOBfill);
+// Resolved through cudaGetDriverEntryPoint so the library has no link-time dependency on libcuda.so.
+TensorMapEncodeTiledFn get_tensor_map_encoder();
+
+// conv3d_tc.cu
+int conv3d_k3_bn(int Cout);
+int conv3d_k3_td(int Cout);
+size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout);
+int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, float* y_raw,
+                  float* stats_partial, int desc_base_mode, cudaStream_t stream);
+int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, const float* bias,
+                     int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream);
+size_t packed_weight_bytes(int Cout, int Cin, int taps, int transposed);
+int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int transposed, cudaStream_t stream);
+
+
+// elementwise.cu
+int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
+                     int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
+                     cudaStream_t stream);
+size_t conv_cin1_stats_tiles(int NB, int D, int H, int W);
+int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, float* y_raw,
+                       float* stats_partial, cudaStream_t stream);
+int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps,
+                      float* mean_rstd, cudaStream_t stream);
+int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
+                  int y_coff, void* pooled, cudaStream_t stream);
+int head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* hp, int NB, int D, int H, int W,
+                         int C, int crop, float* y, cudaStream_t stream);
+int blend_gather_f32(const float* pieces, const long long* piece_off, const int* piece_z0, const int* padded,
+                     const int* steps, int roi, int overlap, int out_z0, int out_nz, float* out, cudaStream_t stream);
+int select_init(const unsigned long long* ranks, void* st, cudaStream_t stream);
+int select_histogram(const float* data, long long n, int pass, const void* st, unsigned long long* hist,
+                     cudaStream_t stream);
+int select_update(int pass, void* st, unsigned long long* hist, cudaStream_t stream);
+int percentile_lerp(const void* st, double t_lo, double t_hi, double* out64, float* out32, cudaStream_t stream);
+int rescale_u16_crop(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3,
+                     int z_begin, int z_count, uint16_t* out, cudaStream_t stream);
+int mip_fwd(const float* vol, int D, int H, int W, int axis, int start, int depth, float* proj, int* argmax,
+            cudaStream_t stream);
+int mip_bwd(const float* gproj, const int* argmax, int D, int H, int W, int axis, float* gvol, cudaStream_t stream);
+
+const char* last_error();
+
+}  // namespace nc

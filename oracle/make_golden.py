@@ -1,0 +1,158 @@
+"""Pins the oracle against the unmodified reference and writes tests/golden/*.npz.
+Test infrastructure — see oracle/__init__.py.  Run in the build container only:  python -m oracle.make_golden
+
+Every fixture stores the INPUT (or the seed that regenerates it) and the output of the REFERENCE code, never of
+the oracle; the script also asserts oracle == reference on the spot.
+"""
+from __future__ import annotations
+
+import io
+import os
+import sys
+import tempfile
+from collections import OrderedDict
+from contextlib import redirect_stdout
+
+import numpy as np
+import torch
+
+from . import assemble, dice, geometry, mip, reference_harness as rh, unet
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _ref_dataset_and_assembler(vol, roi, ov, bc, normalize):
+    rh.install()
+    rh.set_volume(vol)
+    import data as refdata
+    from util.assemble_dice import Assemble_Dice
+    opt = rh.dice_opt(rh.make_dataroot(tempfile.mkdtemp()), roi, ov, bc, normalize)
+    with redirect_stdout(io.StringIO()):
+        ds = refdata.find_dataset_using_name("diceImage")(opt)
+        asm = Assemble_Dice(opt)
+    return ds, asm, opt
+
+
+def golden_geometry():
+    """Geometry KATs from the reference classes themselves."""
+    rows = []
+    for size, roi, ov, bc in [((128, 128, 128), 120, 15, 10), ((31, 40, 27), 12, 3, 2), ((50, 61, 33), 16, 4, 1),
+                              ((105, 210, 120), 120, 15, 10), ((9, 9, 9), 8, 2, 1)]:
+        vol = np.zeros(size, dtype=np.uint16)
+        ds, asm, _ = _ref_dataset_and_assembler(vol, roi, ov, bc, False)
+        g = geometry.dice_geometry(size, roi, ov, bc)
+        assert tuple(ds.size()) == g.padded and tuple(ds.shape()) == g.steps and len(ds) == g.n_cubes, (size, g)
+        assert (asm.z_steps, asm.y_steps, asm.x_steps) == g.steps
+        for i in range(len(ds)):
+            assert tuple(asm.indexToCoordinates(i)) == g.origin(i)
+        rows.append(list(size) + [roi, ov, bc] + list(g.padded) + list(g.steps))
+    # large shapes: formula only (SURVEY KATs: 900^3 -> 960^3 / 9x9x9; (1024,2048,2048) -> 10x20x20)
+    for size in [(900, 900, 900), (1024, 2048, 2048)]:
+        g = geometry.dice_geometry(size, 120, 15, 10)
+        rows.append(list(size) + [120, 15, 10] + list(g.padded) + list(g.steps))
+    assert rows[-2][6:] == [960, 960, 960, 9, 9, 9] and rows[-1][6:] == [1065, 2115, 2115, 10, 20, 20]
+    np.savez_compressed(os.path.join(GOLD, "geometry.npz"), rows=np.array(rows, dtype=np.int64))
+
+
+def golden_dice_assemble():
+    """Non-cubic 31x40x27 uint16 volume, roi 12 / overlap 3 / border 2: reference cubes, blend, final volume."""
+    rng = np.random.default_rng(0)
+    size, roi, ov, bc = (31, 40, 27), 12, 3, 2
+    vol = rng.integers(0, 65536, size, dtype=np.uint16)
+    g = geometry.dice_geometry(size, roi, ov, bc)
+    out = {}
+    for normalize in (True, False):
+        ds, asm, _ = _ref_dataset_and_assembler(vol, roi, ov, bc, normalize)
+        cubes = np.stack([ds[i]["A"].numpy() for i in range(len(ds))])             # (n,1,E,E,E) float32
+        dd = dice.DirectDicer(vol, g)
+        for i in range(g.n_cubes):
+            assert np.array_equal(cubes[i], dd.cube(i)) and np.array_equal(cubes[i], dice.dice_cube_gather(vol, g, i))
+        fake = rng.random(cubes.shape, dtype=np.float32)                             # stand-in network outputs
+        with redirect_stdout(io.StringIO()):
+            for i in range(g.n_cubes):
+                t = torch.from_numpy(fake[i][None])
+                asm.addToStack(OrderedDict(real=t, fake=t))
+            asm.assemble_all()
+        ref_final = asm.getDict()["fake"]
+        mine, pcts = assemble.assemble(list(fake), g, normalize)
+        assert ref_final.dtype == np.uint16 and np.array_equal(ref_final, mine)
+        out["final_norm" if normalize else "final_plain"] = ref_final
+        if normalize:
+            out["pcts"] = np.array(pcts)
+        else:
+            vis, mask = assemble.blend_sequential([assemble.crop_border(c, bc) for c in fake], g)
+            assert np.array_equal(mask, asm.getMaskRet() if "real" in asm.mask_ret else mask)
+            assert np.array_equal(mask, assemble.analytic_count(g))
+            out["blend"] = vis
+    out.update(volume=vol, cubes=cubes, fake=fake, params=np.array([roi, ov, bc]))
+    np.savez_compressed(os.path.join(GOLD, "dice_assemble_31x40x27.npz"), **out)
+
+
+def golden_unet():
+    """Reference Unet_deconv (networks.define_G) vs oracle on a 16^3 and a 24x16x20 input, shared state_dict."""
+    rh.install()
+    from models import networks
+    torch.manual_seed(0)
+    net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
+    net.eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == unet.STATE_DICT_SHAPES
+    assert sum(v.numel() for v in sd.values()) == unet.N_PARAMS
+    # biases are zero at init; perturb them so bias handling is covered
+    g = torch.Generator().manual_seed(1)
+    for k in sd:
+        if k.endswith("bias"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+    net.load_state_dict(sd)
+    out = {}
+    for name, shape in (("a", (1, 1, 16, 16, 16)), ("b", (1, 1, 24, 16, 20))):
+        x = torch.rand(shape, generator=g)
+        with torch.no_grad():
+            y_ref = net(x)
+        y_or = unet.unet_deconv_forward(x, sd)
+        err = (y_ref - y_or).abs().max().item()
+        assert err <= 1e-6, err
+        out["x_" + name], out["y_" + name] = x.numpy(), y_ref.numpy()
+    # weights are regenerated from the seed in the test; store a checksum and a few slices instead of 28 MB
+    out["w_checksum"] = np.array([float(sum(v.double().sum() for v in sd.values())),
+                                  float(sum(v.double().abs().sum() for v in sd.values()))])
+    torch.save(sd, os.path.join(GOLD, "_unet_state_dict.pt"))   # git-ignored helper (28 MB); see below
+    np.savez_compressed(os.path.join(GOLD, "unet_small.npz"), **out)
+
+
+def golden_mip():
+    rh.install()
+    from models.axial_to_lateral_gan_apollo_model import Volume
+    g = torch.Generator().manual_seed(3)
+    vol = torch.rand((1, 1, 12, 12, 12), generator=g)
+    out = {"vol": vol.numpy()}
+    np.random.seed(5)
+    state = np.random.get_state()
+    for axis in range(3):
+        np.random.set_state(state)
+        ref = Volume(vol, torch.device("cpu")).get_projection(4, axis)
+        np.random.set_state(state)
+        mine, start = mip.get_projection(vol, 4, axis)
+        assert torch.equal(ref, mine)
+        out[f"proj{axis}"], out[f"start{axis}"] = ref.numpy(), np.array(start)
+        np.random.set_state(state)
+        ref_s = Volume(vol, torch.device("cpu")).get_slice(axis)
+        np.random.set_state(state)
+        mine_s, idx = mip.get_slice(vol, axis)
+        assert torch.equal(ref_s, mine_s)
+    np.savez_compressed(os.path.join(GOLD, "mip_12.npz"), **out)
+
+
+def main():
+    if not rh.available():
+        sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
+    os.makedirs(GOLD, exist_ok=True)
+    golden_geometry()
+    golden_dice_assemble()
+    golden_unet()
+    golden_mip()
+    print("golden vectors written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
