@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — voxels/s of diced unet_deconv inference on a synthetic 900^3 16-bit volume (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over the whole volume (729 cubes of 140^3 -> blend -> percentile stretch ->
+uint16).  `value` is timed with the uint16 volume already resident in HBM; `e2e` goes through the public API
+(DicedInference.run) with the pinned-host -> device copy of the volume and the device -> host copy of the result
+inside the timed region.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max
+over ranks.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxels/sec diced unet_deconv inference, 900^3 vol"
+UNIT = "voxels/s"
+PUBLISHED_VOXELS_PER_S = 1.84e6   # 729 cubes at 1.84 it/s on the author's GPU (screenshot)
+ROI, OVERLAP, BORDER = 120, 15, 10
+
+
+def synthetic_volume(shape, seed=0):
+    """uniform random uint16 volume (the reference's generator notebook is a missing blob)."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 65536, shape, dtype=np.uint16)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md, sustained ~1.4 PFLOP/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline_sample(shape, threads=None):
+    """The oracle (port of the reference's CPU path) on a bounded sample of the workload: one of the n cubes through
+    dice + Unet_deconv fp32 forward, and the blend/percentile/rescale stage on a 2x2x2-cube (225^3 padded) volume
+    scaled by cube count.  Returns (voxels_per_s, cores, sample description, seconds spent)."""
+    from oracle import assemble, dice, geometry as ogeo, unet as ounet
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    g = ogeo.dice_geometry(shape, ROI, OVERLAP, BORDER)
+    sd = ounet.random_state_dict(seed=0)
+    small = synthetic_volume((128, 128, 128), seed=1)
+    gs = ogeo.dice_geometry(small.shape, ROI, OVERLAP, BORDER)
+    t0 = time.perf_counter()
+    x = torch.from_numpy(dice.dice_cube_gather(small, gs, 0))[None]
+    y = ounet.unet_deconv_forward(x, sd)
+    t_cube = time.perf_counter() - t0
+    cube = assemble.crop_border(y.numpy(), BORDER)
+    t0 = time.perf_counter()
+    vis, _ = assemble.blend_sequential([cube] * gs.n_cubes, gs)
+    assemble.finish(vis, gs, True)
+    t_asm = (time.perf_counter() - t0) * g.n_cubes / gs.n_cubes
+    total = g.n_cubes * t_cube + t_asm
+    voxels = float(np.prod(shape))
+    sample = ("1 of %d cubes (dice + Unet_deconv fp32 forward, %.2f s) + blend/percentile/rescale of an 8-cube volume "
+              "scaled x%d/8 (%.2f s), extrapolated to the whole volume" % (g.n_cubes, t_cube, g.n_cubes, t_asm))
+    return voxels / total, cores, sample, t_cube + t_asm * gs.n_cubes / g.n_cubes
+
+
+def run_reference(args, shape):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, t_wall = [], []
+    for i in range(args.warmup + args.steps):
+        v, cores, sample, secs = cpu_baseline_sample(shape)
+        if i >= args.warmup:
+            vals.append(v)
+            t_wall.append(secs)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.prod(shape)) / value * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(shape, None, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = the oracle port of the reference's CPU path (torch CPU fp32 + numpy) on all host threads; "
+                "the Python reference itself cannot travel to the GPU box; each step is a bounded sample, ms_per_step "
+                "is the extrapolated whole-volume time",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(shape, batch, gpus):
+    return {"workload": "test_dice.py unet_deconv inference, synthetic %dx%dx%d uint16 volume, dice %d overlap %d "
+                        "border_cut %d, normalize_intensity (0.25, 99.75)" % (*shape, ROI, OVERLAP, BORDER),
+            "cubes": None, "batch_cubes": batch, "parallelism": "cube-range x%d + z-slab assembly" % gpus,
+            "l2": "inputs larger than L2 (1.46 GB volume, >2 GB of activations per batch)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, nargs=3, default=[900, 900, 900])
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    shape = tuple(args.size)
+
+    if args.impl == "reference":
+        return run_reference(args, shape)
+
+    import torch.distributed as dist
+    from neuroclear_b200 import _lib
+    from neuroclear_b200.pipeline import DicedInference
+    from neuroclear_b200.unet_engine import FLOP_PER_VOXEL
+    from oracle import unet as ounet   # weights only: the seeded random-init state_dict shared with the oracle
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N>1)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sd = ounet.random_state_dict(seed=0)
+    pipe = DicedInference(sd, dev, ROI, OVERLAP, BORDER, normalize_intensity=True, batch=args.batch)
+    plan = pipe.plan(shape)
+    geo = plan["geo"]
+    z0, z1 = plan["in_planes"]
+    # every rank generates the same volume and keeps only its planes (a real run would read its slab from disk)
+    vol_host = torch.from_numpy(synthetic_volume(shape)).pin_memory()
+    vol_dev = vol_host[z0:z1].to(dev)
+    o0, o1 = plan["out_planes"]
+    out_host = torch.empty((o1 - o0, shape[1], shape[2]), dtype=torch.uint16).pin_memory()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = _lib.LAUNCHES
+        pipe.engine.profile = [] if profile else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        prof, pipe.engine.profile = pipe.engine.profile, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks, _lib.LAUNCHES - launches0, prof
+
+    resident = lambda: pipe.run_device(vol_dev, z0, shape)
+    e2e = lambda: pipe.run(vol_host, out_host)
+
+    for _ in range(args.warmup):
+        resident()
+    ms, clocks, launches, prof = timed(resident, args.steps, profile=True)
+    voxels = float(np.prod(shape))
+    value = voxels * args.steps / (ms * 1e-3)
+
+    # live roofline of the dominant kernel family (tcgen05 implicit-GEMM conv): algorithmic FLOPs / event time
+    peak, peak_src = measured_peaks()
+    layers = {}
+    for name, flops, a, b in prof:
+        t = layers.setdefault(name, [0.0, 0.0, 0])
+        t[0] += flops
+        t[1] += a.elapsed_time(b)
+        t[2] += 1
+    tot_f = sum(v[0] for v in layers.values())
+    tot_ms = sum(v[1] for v in layers.values())
+    achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel (9 Conv3d k3 layers U2..U12, per-launch average)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "launches": sum(v[2] for v in layers.values()),
+                "share_of_step": tot_ms / ms,
+                "layers": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_launch": v[1] / v[2]}
+                           for k, v in layers.items()}}
+
+    for _ in range(1):
+        e2e()
+    ms_e, clocks_e, _, _ = timed(e2e, args.steps)
+    e2e_value = voxels * args.steps / (ms_e * 1e-3)
+    in_bytes = (z1 - z0) * shape[1] * shape[2] * 2
+    out_bytes = (o1 - o0) * shape[1] * shape[2] * 2
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_baseline_sample(shape)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        cfg = workload_config(shape, args.batch, world)
+        cfg["cubes"] = geo.n_cubes
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": ms_e / args.steps, "clocks": clocks_e},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "tensor_pipe_frac_whole_step": FLOP_PER_VOXEL * geo.n_cubes * geo.edge ** 3 * args.steps
+                                            / (ms * 1e-3) / 1e12 / peak / world,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

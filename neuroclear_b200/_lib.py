@@ -1,0 +1,93 @@
+"""ctypes binding of libneuroclear_b200.so (the C ABI declared in include/neuroclear_b200.h).
+
+The library is built in-tree by ``neuroclear_b200.build`` (nvcc, sm_100a).  There is no fallback: if the shared
+object is missing, or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libneuroclear_b200.so")
+
+i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
+I3 = C.c_int32 * 3
+U4 = C.c_uint64 * 4
+
+# name -> (restype, argtypes); mirrors include/neuroclear_b200.h one to one
+SIGNATURES = {
+    "nc_abi_version": (C.c_int, []),
+    "nc_last_error": (C.c_char_p, []),
+    "nc_device_sm_count": (C.c_int, []),
+    "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),
+    "nc_dice_extract_u16": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),
+    "nc_conv3d_k3_stats_rows": (i64, [i32, i32, i32, i32, i32, i32]),
+    "nc_conv3d_cin1_k3_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "nc_packed_weight_bytes": (i64, [i32, i32, i32]),
+    "nc_pack_weights_conv3d_k3": (C.c_int, [vp, i32, i32, vp, vp]),
+    "nc_pack_weights_convT3d_k2s2": (C.c_int, [vp, i32, i32, vp, vp]),
+    "nc_conv3d_k3_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
+    "nc_convT3d_k2s2_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
+    "nc_in_stats_finalize": (C.c_int, [vp, i32, i64, i32, i64, f32, vp, vp]),
+    "nc_in_relu_apply": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "nc_head_1x1_sigmoid_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "nc_blend_gather_f32": (C.c_int, [vp, vp, vp, I3, I3, i32, i32, i32, i32, vp, vp]),
+    "nc_select_init": (C.c_int, [U4, vp, vp]),
+    "nc_select_histogram": (C.c_int, [vp, i64, i32, vp, vp, vp]),
+    "nc_select_update": (C.c_int, [i32, vp, vp, vp]),
+    "nc_percentile_lerp": (C.c_int, [vp, f64, f64, vp, vp, vp]),
+    "nc_rescale_u16_crop": (C.c_int, [vp, i32, I3, I3, vp, i32, i32, vp, vp]),
+    "nc_mip_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "nc_mip_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+}
+
+_lib = None
+
+
+class NeuroclearError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises NeuroclearError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NeuroclearError(
+                f"{LIB_PATH} is missing: build it with `python -m neuroclear_b200.build` "
+                "(there is no CPU or PyTorch fallback for the CUDA hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.nc_abi_version() != 1:
+            raise NeuroclearError("libneuroclear_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise NeuroclearError(load().nc_last_error().decode())
+
+
+#: number of kernel launches issued through `call` (every int-returning entry point launches exactly one kernel)
+LAUNCHES = 0
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point (one kernel launch) and raise on error."""
+    global LAUNCHES
+    check(getattr(load(), name)(*args))
+    LAUNCHES += 1
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -507,9 +507,10 @@ __global__ void select_update_kernel(int pass, SelectState* st, unsigned long lo
 // numpy _lerp on float32 order statistics with float64 gamma (numpy/lib/_function_base_impl.py):
 //   diff = f32(b - a);  r = a + diff*t;  if t >= 0.5: r = b - diff*(1-t)      (r, t in float64)
 __device__ inline double np_lerp(float a, float b, double t) {
+  // separate multiply and add (no FMA contraction): numpy rounds the product before the sum
   const float diff = __fsub_rn(b, a);
-  double r = static_cast<double>(a) + static_cast<double>(diff) * t;
-  if (t >= 0.5) r = static_cast<double>(b) - static_cast<double>(diff) * (1.0 - t);
+  double r = __dadd_rn(static_cast<double>(a), __dmul_rn(static_cast<double>(diff), t));
+  if (t >= 0.5) r = __dsub_rn(static_cast<double>(b), __dmul_rn(static_cast<double>(diff), __dsub_rn(1.0, t)));
   return r;
 }
 __global__ void percentile_lerp_kernel(const SelectState* st, double t_lo, double t_hi, double* out64, float* out32) {

@@ -1,0 +1,314 @@
+"""Drop-ins for the reference's ``data/diceImage_dataset.py`` and ``util/assemble_dice.py`` on the C ABI.
+
+Same class names, constructor (``opt`` namespace), methods and attributes as the reference
+(diceImage_dataset.py:9-79, assemble_dice.py:11-244), but the volume lives in HBM: cubes are cut by
+``nc_dice_extract_u16`` (zero pad + reflect border + /65535 fused, no padded copies) and the assembly runs
+``nc_blend_gather_f32`` / radix-select percentile / ``nc_rescale_u16_crop`` on the device.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import I3, U4, NeuroclearError, call, i64, ptr, stream_ptr
+
+
+# ---------------------------------------------------------------------------------------------- geometry
+@dataclass(frozen=True)
+class DiceGeometry:
+    size: tuple      # original (Z, Y, X)
+    padded: tuple    # util.pad_for_dicing result
+    steps: tuple     # cubes per axis (z, y, x)
+    roi: int
+    overlap: int
+    border: int
+
+    @property
+    def step(self):
+        return self.roi - self.overlap
+
+    @property
+    def edge(self):
+        return self.roi + 2 * self.border
+
+    @property
+    def n_cubes(self):
+        return self.steps[0] * self.steps[1] * self.steps[2]
+
+    def c_arrays(self):
+        return I3(*self.size), I3(*self.padded), I3(*self.steps)
+
+
+def dice_geometry(size, roi: int, overlap: int, border: int = 0) -> DiceGeometry:
+    """util/util.py:196-215 + diceImage_dataset.py:90-92, computed by the library (nc_dice_geometry)."""
+    padded, steps = I3(), I3()
+    n = _lib.load().nc_dice_geometry(I3(*[int(s) for s in size]), roi, overlap, padded, steps)
+    if n < 0:
+        raise NeuroclearError(_lib.load().nc_last_error().decode())
+    return DiceGeometry(tuple(int(s) for s in size), tuple(padded), tuple(steps), roi, overlap, border)
+
+
+# ---------------------------------------------------------------------------------------------- device ops
+def dice_extract(vol_dev: torch.Tensor, vol_z0: int, geo: DiceGeometry, cube_begin: int, count: int,
+                 out: torch.Tensor = None) -> torch.Tensor:
+    """vol_dev: uint16 CUDA planes [vol_z0, vol_z0+n) of the original volume -> float32 (count, E, E, E)."""
+    if not vol_dev.is_cuda:
+        raise NeuroclearError("dice_extract: the volume must be in device memory (no CPU fallback)")
+    assert vol_dev.dtype == torch.uint16 and vol_dev.is_contiguous()
+    e = geo.edge
+    if out is None:
+        out = torch.empty((count, e, e, e), dtype=torch.float32, device=vol_dev.device)
+    size, padded, steps = geo.c_arrays()
+    call("nc_dice_extract_u16", ptr(vol_dev), vol_z0, vol_dev.shape[0], size, padded, steps, geo.roi, geo.overlap,
+         geo.border, i64(cube_begin), count, ptr(out), stream_ptr())
+    return out
+
+
+def blend_gather(pieces, piece_off, piece_z0, geo: DiceGeometry, z0: int, nz: int, out=None):
+    if out is None:
+        out = torch.empty((nz, geo.padded[1], geo.padded[2]), dtype=torch.float32, device=pieces.device)
+    _, padded, steps = geo.c_arrays()
+    call("nc_blend_gather_f32", ptr(pieces), ptr(piece_off), ptr(piece_z0), padded, steps, geo.roi, geo.overlap,
+         z0, nz, ptr(out), stream_ptr())
+    return out
+
+
+def percentile_ranks(n_total: int, sat_level):
+    """numpy 'linear' method index arithmetic (np.percentile -> _quantile): virtual index (n-1)*q/100 in fp64."""
+    q = np.true_divide(np.asarray(sat_level, dtype=np.float64), 100)
+    virt = (n_total - 1) * q
+    prev = np.floor(virt)
+    gamma = virt - prev
+    lo = prev.astype(np.int64)
+    hi = np.minimum(lo + 1, n_total - 1)
+    return [int(lo[0]), int(hi[0]), int(lo[1]), int(hi[1])], float(gamma[0]), float(gamma[1])
+
+
+class PercentileSelect:
+    """Exact np.percentile(vis, (p_lo, p_hi)) on the device; optionally all-reduces histograms over a group."""
+
+    def __init__(self, device):
+        self.state = torch.zeros(64, dtype=torch.uint8, device=device)          # SelectState
+        self.hist = torch.zeros(4 * 4096, dtype=torch.int64, device=device)     # uint64 [4][4096]
+        self.out64 = torch.zeros(2, dtype=torch.float64, device=device)
+        self.norm3 = torch.zeros(3, dtype=torch.float32, device=device)
+
+    def run(self, data: torch.Tensor, n_total: int, sat_level, group=None, distributed=False):
+        ranks, t_lo, t_hi = percentile_ranks(n_total, sat_level)
+        s = stream_ptr()
+        self.hist.zero_()
+        call("nc_select_init", U4(*ranks), ptr(self.state), s)
+        for p in range(3):
+            call("nc_select_histogram", ptr(data), i64(data.numel()), p, ptr(self.state), ptr(self.hist), s)
+            if distributed:
+                torch.distributed.all_reduce(self.hist, group=group)
+            call("nc_select_update", p, ptr(self.state), ptr(self.hist), s)
+        call("nc_percentile_lerp", ptr(self.state), t_lo, t_hi, ptr(self.out64), ptr(self.norm3), s)
+        return self.norm3, self.out64
+
+
+def rescale_u16_crop(vis: torch.Tensor, vis_z0: int, geo: DiceGeometry, norm3, z_begin: int, z_count: int, out=None):
+    if out is None:
+        out = torch.empty((z_count, geo.size[1], geo.size[2]), dtype=torch.uint16, device=vis.device)
+    size, padded, _ = geo.c_arrays()
+    call("nc_rescale_u16_crop", ptr(vis), vis_z0, padded, size, ptr(norm3), z_begin, z_count, ptr(out), stream_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- dataset
+def _load_volume(path):
+    """Volume I/O is outside the hot path; .npy always works, TIFF stacks through cv2."""
+    if os.path.isdir(path):
+        names = sorted(f for f in os.listdir(path) if not f.startswith(".") and
+                       f.lower().endswith((".npy", ".tif", ".tiff")))
+        if not names:
+            raise FileNotFoundError("no .npy/.tif volume under %s" % path)
+        path = os.path.join(path, names[0])
+    if path.lower().endswith(".npy"):
+        return np.load(path)
+    import cv2
+    ok, pages = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)
+    if not ok:
+        raise IOError("cannot read %s" % path)
+    return np.stack(pages)
+
+
+class DiceImageDataSet:
+    """reference data/diceImage_dataset.py:9-79 — one volume, one cube per index (x fastest, then y, then z)."""
+
+    @staticmethod
+    def modify_commandline_options(parser, is_train=False):
+        parser.add_argument("--overlap", type=int, default=0,
+                            help="set the size of overlapping region when dicing the dataset.")
+        parser.add_argument("--border_cut", default=0, type=int,
+                            help="specify how much border you want to remove in a cube-by-cube inference.")
+        return parser
+
+    def __init__(self, opt, volume: np.ndarray = None):
+        self.opt = opt
+        self.roi_size = opt.dice_size[0]
+        self.overlap = opt.overlap
+        self.border_cut = opt.border_cut
+        vol = volume if volume is not None else _load_volume(opt.dataroot)
+        if vol.dtype != np.uint16:
+            raise NeuroclearError("the B200 dice path takes 16-bit volumes (--data_type uint16)")
+        if "addColorChannel" not in getattr(opt, "preprocess", "addColorChannel"):
+            raise NeuroclearError("DiceImageDataSet expects --preprocess addColorChannel as in the reference README")
+        gpu_ids = getattr(opt, "gpu_ids", [0])
+        self.device = torch.device("cuda", gpu_ids[0] if gpu_ids else 0)
+        self.geo = dice_geometry(vol.shape, self.roi_size, self.overlap, self.border_cut)
+        self.image_size_original = tuple(vol.shape)
+        self.image_size = self.geo.padded
+        self.host_volume = vol
+        self._dev = None
+        self.A_path = getattr(opt, "dataroot", "")
+
+    def device_volume(self) -> torch.Tensor:
+        if self._dev is None:
+            self._dev = torch.from_numpy(np.ascontiguousarray(self.host_volume)).to(self.device)
+        return self._dev
+
+    def cubes(self, begin: int, count: int, out=None) -> torch.Tensor:
+        """Batched accessor used by the fast path: float32 (count, E, E, E) on the device."""
+        with torch.cuda.device(self.device):
+            return dice_extract(self.device_volume(), 0, self.geo, begin, count, out)
+
+    def __getitem__(self, index):
+        if index < 0 or index >= len(self):
+            raise IndexError(index)
+        return {"A": self.cubes(index, 1), "A_paths": str(index)}   # (1, E, E, E): colour channel added
+
+    def __len__(self):
+        return self.geo.n_cubes
+
+    def __iter__(self):
+        """Iterating yields batch-1 items like the reference's DataLoader: A is (1, 1, E, E, E)."""
+        for i in range(len(self)):
+            item = self[i]
+            yield {"A": item["A"][None], "A_paths": [item["A_paths"]]}
+
+    def shape(self):
+        return self.geo.steps
+
+    def size(self):
+        return self.image_size
+
+    def size_original(self):
+        return self.image_size_original
+
+
+# ---------------------------------------------------------------------------------------------- assembly
+class Assemble_Dice:
+    """reference util/assemble_dice.py:11-244 — queue border-cut cubes, blend, normalise, cast, un-pad."""
+
+    def __init__(self, opt, dataset: DiceImageDataSet = None):
+        ds = dataset if dataset is not None else DiceImageDataSet(opt)
+        self.geo = ds.geo
+        self.device = ds.device
+        self.image_size_original = ds.size_original()
+        self.image_size = ds.size()
+        self.border_cut = opt.border_cut
+        self.roi_size = opt.dice_size[0]
+        self.overlap = opt.overlap
+        self.step = self.roi_size - self.overlap
+        self.z_steps, self.y_steps, self.x_steps = self.geo.steps
+        self.visual_names = ["real", "fake"]
+        self.imtype = opt.data_type
+        if self.imtype != "uint16":
+            raise NeuroclearError("Assemble_Dice (B200): only --data_type uint16 is implemented")
+        self.skip_real = opt.skip_real
+        if getattr(opt, "histogram_match", False):
+            raise NotImplementedError("--histogram_match is outside the B200 hot path (SURVEY.md §8f-3)")
+        self.normalize_intensity = opt.normalize_intensity
+        if self.normalize_intensity:
+            self.p1, self.p99 = opt.sat_level
+        if self.border_cut < 1:
+            raise NeuroclearError("border_cut must be >= 1 (the reference's [bc:-bc] crop is empty for 0)")
+        if self.overlap <= 0:
+            raise NeuroclearError("overlap must be > 0 (the reference assembles all zeros otherwise)")
+        self.len_cube_queue = self.geo.n_cubes
+        self.visual_ret = OrderedDict()
+        self.snapDict = OrderedDict()
+        self.cube_queue = OrderedDict()
+        self.percentiles = {}
+        self._count = {}
+        r = self.roi_size
+        for name in self.visual_names:
+            if self.skip_real and name == "real":
+                continue
+            self.cube_queue[name] = torch.empty((self.len_cube_queue, r, r, r), dtype=torch.float32,
+                                                device=self.device)
+            self._count[name] = 0
+
+    def indexTo3DIndex(self, index):
+        x = index % self.x_steps
+        y = (index % (self.x_steps * self.y_steps)) // self.x_steps
+        z = index // (self.x_steps * self.y_steps)
+        return z, y, x
+
+    def indexToCoordinates(self, index):
+        z, y, x = self.indexTo3DIndex(index)
+        return z * self.step, y * self.step, x * self.step
+
+    def addToStack(self, cube):
+        """cube: dict with 'real' and 'fake' (1,1,E,E,E) tensors, as BaseModel.get_current_visuals() returns."""
+        bc = self.border_cut
+        for name in self.visual_names:
+            t = cube[name]                       # both keys are required, like the reference (:132-133)
+            if self.skip_real and name == "real":
+                continue
+            if not t.is_cuda:
+                raise NeuroclearError("Assemble_Dice (B200) takes device tensors; there is no CPU assembly path")
+            c = t.reshape(t.shape[-3:])[bc:-bc, bc:-bc, bc:-bc]
+            assert tuple(c.shape) == (self.roi_size,) * 3, "the cube dimensions are invalid."
+            i = self._count[name]
+            if i >= self.len_cube_queue:
+                raise NeuroclearError("more cubes added than the volume has")
+            self.cube_queue[name][i].copy_(c)
+            self._count[name] = i + 1
+
+    def queue_view(self, name="fake"):
+        """Device queue (n_cubes, roi, roi, roi): the fast path lets the network head write into it directly."""
+        return self.cube_queue[name]
+
+    def mark_filled(self, name="fake"):
+        self._count[name] = self.len_cube_queue
+
+    def assemble_all(self):
+        g = self.geo
+        r3 = self.roi_size ** 3
+        with torch.cuda.device(self.device):
+            off = torch.arange(g.n_cubes, dtype=torch.int64, device=self.device) * r3
+            z0 = torch.zeros(g.n_cubes, dtype=torch.int32, device=self.device)
+            sel = PercentileSelect(self.device) if self.normalize_intensity else None
+            for name, queue in self.cube_queue.items():
+                if self._count[name] != self.len_cube_queue:
+                    raise NeuroclearError("assemble_all: %d of %d cubes queued for '%s'" %
+                                          (self._count[name], self.len_cube_queue, name))
+                vis = blend_gather(queue.view(-1), off, z0, g, 0, g.padded[0])
+                norm3 = None
+                if self.normalize_intensity:
+                    norm3, p64 = sel.run(vis, vis.numel(), (self.p1, self.p99))
+                    self.percentiles[name] = p64
+                out = rescale_u16_crop(vis, 0, g, norm3, 0, g.size[0])
+                del vis
+                self.visual_ret[name] = out.cpu().numpy()
+                if name in self.percentiles:
+                    self.percentiles[name] = tuple(self.percentiles[name].cpu().tolist())
+
+    def getSnapshots(self, index, slice_axis=2):
+        for name in self.visual_ret:
+            v = self.visual_ret[name]
+            self.snapDict[name] = v[index] if slice_axis == 0 else v[:, index] if slice_axis == 1 else v[:, :, index]
+        return self.snapDict
+
+    def getDict(self):
+        return self.visual_ret
+
+    def getCubeQueue(self):
+        return self.cube_queue

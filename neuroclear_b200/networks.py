@@ -1,0 +1,156 @@
+"""Drop-in for the reference's ``models/networks.py`` on the unet_deconv path.
+
+``define_G(..., netG='unet_deconv')`` (reference networks.py:140-197) returns an ``nn.Module`` with exactly the
+reference's state_dict (28 tensors, same keys / shapes / OIDHW + IODHW layouts), initialised by the same
+``init_weights`` rule (networks.py:88-119), whose ``forward`` runs the hand-written sm_100a kernels through the C
+ABI.  The ``nn.Conv3d`` / ``nn.ConvTranspose3d`` children are parameter containers only — they keep checkpoints,
+optimisers and ``print_networks`` working — and are never called.
+"""
+from __future__ import annotations
+
+import functools
+
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+from ._lib import NeuroclearError
+from .unet_engine import UnetDeconvEngine
+
+
+class Identity(nn.Module):
+    def forward(self, x):
+        return x
+
+
+def get_norm_layer(norm_type="instance", dimension=3):
+    """reference networks.py:20-44"""
+    inorm = {1: nn.InstanceNorm1d, 2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}[dimension]
+    bnorm = {1: nn.BatchNorm1d, 2: nn.BatchNorm2d, 3: nn.BatchNorm3d}[dimension]
+    if norm_type == "batch":
+        return functools.partial(bnorm, affine=True, track_running_stats=True)
+    if norm_type == "instance":
+        return functools.partial(inorm, affine=False, track_running_stats=False)
+    if norm_type in ("spectral", "none"):
+        return lambda x: Identity()
+    raise NotImplementedError("normalization layer [%s] is not found" % norm_type)
+
+
+def init_weights(net, init_type="normal", init_gain=0.02):
+    """reference networks.py:88-119 (same class-name matching, same initialisers)."""
+    def init_func(m):
+        classname = m.__class__.__name__
+        if hasattr(m, "weight") and (classname.find("Conv") != -1 or classname.find("Linear") != -1):
+            if init_type == "normal":
+                init.normal_(m.weight.data, 0.0, init_gain)
+            elif init_type == "xavier":
+                init.xavier_normal_(m.weight.data, gain=init_gain)
+            elif init_type == "kaiming":
+                init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "orthogonal":
+                init.orthogonal_(m.weight.data, gain=init_gain)
+            else:
+                raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+            if hasattr(m, "bias") and m.bias is not None:
+                init.constant_(m.bias.data, 0.0)
+        elif classname.find("BatchNorm") != -1:
+            init.normal_(m.weight.data, 1.0, init_gain)
+            init.constant_(m.bias.data, 0.0)
+
+    print("initialize network with %s" % init_type)
+    net.apply(init_func)
+
+
+def init_net(net, init_type="normal", init_gain=0.02, gpu_ids=[]):
+    """reference networks.py:122-137.  One process drives one GPU here, so a non-empty gpu_ids moves the net to
+    gpu_ids[0] and wraps it in a single-device DataParallel: BaseModel.save_networks / load_networks
+    (base_model.py:158-160,189-190) unwrap ``.module`` exactly as with the reference."""
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.to(gpu_ids[0])
+        net = torch.nn.DataParallel(net, [gpu_ids[0]])
+    init_weights(net, init_type, init_gain=init_gain)
+    return net
+
+
+def _conv_block(n_convs, cin, cout, norm_layer):
+    """Same child indices as double_conv / triple_conv / last_conv (networks.py:413-476): conv at 0, 3, 6."""
+    layers = []
+    for i in range(n_convs):
+        layers += [nn.Conv3d(cin if i == 0 else cout, cout, 3, 1, 1), norm_layer(cout), nn.ReLU()]
+    return layers
+
+
+class _ConvStack(nn.Module):
+    def __init__(self, n_convs, cin, cout, norm_layer):
+        super().__init__()
+        self.convolution = nn.Sequential(*_conv_block(n_convs, cin, cout, norm_layer))
+
+
+class Unet_deconv(nn.Module):
+    """reference networks.py:478-538; forward on sm_100a kernels (inference only for now)."""
+
+    def __init__(self, input_nc, output_nc, norm_layer=None, dimension=3):
+        super().__init__()
+        if dimension != 3 or input_nc != 1 or output_nc != 1:
+            raise NotImplementedError("the B200 path implements the 3-D, 1-channel unet_deconv of the reference")
+        norm_layer = norm_layer or get_norm_layer("instance", 3)
+        probe = norm_layer(1)
+        if not isinstance(probe, nn.InstanceNorm3d) or probe.affine or probe.track_running_stats:
+            raise NotImplementedError("unet_deconv on B200 is built for --norm instance (affine=False), as in the "
+                                      "reference's README commands")
+        nc = input_nc * 64
+        self.double_conv1 = _ConvStack(2, input_nc, nc, norm_layer)
+        self.double_conv2 = _ConvStack(2, nc, nc * 2, norm_layer)
+        self.bottom_layer = _ConvStack(3, nc * 2, nc * 4, norm_layer)
+        self.t_conv2 = nn.ConvTranspose3d(nc * 4, nc * 2, 2, 2)
+        self.ex_double_conv2 = _ConvStack(2, nc * 4, nc * 2, norm_layer)
+        self.t_conv1 = nn.ConvTranspose3d(nc * 2, nc, 2, 2)
+        self.ex_conv1_1 = _ConvStack(1, nc * 2, nc, norm_layer)
+        self.one_by_one = nn.Conv3d(nc, output_nc, 1, 1, 0)
+        self.one_by_one_2 = nn.Conv3d(output_nc, output_nc, 1, 1, 0)
+        self._engine = None
+        self._engine_sig = None
+
+    # the packed bf16 weight cache follows the parameters: any in-place update, load_state_dict or device move
+    # changes (data_ptr, _version) and triggers a repack on the next forward.
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self) -> UnetDeconvEngine:
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise NeuroclearError("Unet_deconv (B200): parameters are on the CPU; there is no CPU fallback — "
+                                  "move the network to a CUDA device")
+        sig = self._signature()
+        if self._engine is None or self._engine.device != p.device:
+            self._engine, self._engine_sig = UnetDeconvEngine(p.device), None
+        if self._engine_sig != sig:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_sig = sig
+        return self._engine
+
+    def forward(self, inputs):
+        if torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in self.parameters())) \
+                and self.training:
+            raise NotImplementedError("autograd through the B200 unet_deconv path is not implemented yet; "
+                                      "call it under torch.no_grad() / model.eval()")
+        if inputs.dim() != 5 or inputs.shape[1] != 1:
+            raise NeuroclearError("Unet_deconv expects (N, 1, D, H, W)")
+        if not inputs.is_cuda:
+            raise NeuroclearError("Unet_deconv (B200): input is on the CPU; there is no CPU fallback")
+        eng = self.engine()
+        with torch.cuda.device(inputs.device):
+            x = inputs.detach().to(torch.float32)[:, 0].contiguous()
+            return eng.forward(x)[:, None]
+
+
+def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, init_type="normal", init_gain=0.02,
+             gpu_ids=[], kernel_size=9, given_psf=None, noise_setting=None, dimension=3):
+    """reference networks.py:140-197; only the generator on the hot path is provided."""
+    norm_layer = get_norm_layer(norm_type=norm, dimension=dimension)
+    if netG == "unet_deconv":
+        net = Unet_deconv(1, output_nc, norm_layer=norm_layer, dimension=dimension)  # input_nc hard-coded 1 (:174)
+    else:
+        raise NotImplementedError("Generator model name [%s] is not on the B200 hot path (only unet_deconv is)" % netG)
+    return init_net(net, init_type, init_gain, gpu_ids)

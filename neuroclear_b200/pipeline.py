@@ -1,0 +1,128 @@
+"""Whole-volume diced inference (the loop of the reference's test_dice.py:70-121) as one device-resident pipeline:
+
+    host uint16 volume --H2D--> dice (fused pad/reflect/normalise) --> Unet_deconv on batches of cubes
+      --> border-cut outputs in an HBM queue --> [piece exchange over NVLink when sharded]
+      --> gather-blend --> exact percentile (radix select, histogram all-reduce) --> rescale/cast/un-pad --D2H--> host
+
+One process drives one GPU.  With a process group, cubes are split into balanced contiguous index ranges and the
+assembled volume into balanced z-slabs (neuroclear_b200.sharding); results are value-identical for any world
+size because the blend always runs in ascending cube index on the slab owner.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import sharding
+from ._lib import NeuroclearError
+from .dicing import (DiceGeometry, PercentileSelect, blend_gather, dice_extract, dice_geometry, rescale_u16_crop)
+from .unet_engine import UnetDeconvEngine
+
+
+class DicedInference:
+    def __init__(self, state_dict, device, roi=120, overlap=15, border=10, normalize_intensity=True,
+                 sat_level=(0.25, 99.75), batch=4, group=None, distributed=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NeuroclearError("DicedInference needs a CUDA device (no CPU fallback)")
+        if border < 1 or overlap < 1 or 2 * overlap > roi:
+            raise NeuroclearError("need border_cut >= 1 and 0 < overlap <= roi - overlap (as the reference's assembly)")
+        self.roi, self.overlap, self.border = roi, overlap, border
+        self.normalize_intensity, self.sat_level = normalize_intensity, tuple(sat_level)
+        self.batch = batch
+        self.group = group
+        self.distributed = dist.is_initialized() if distributed is None else distributed
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        with torch.cuda.device(self.device):
+            self.engine = UnetDeconvEngine(self.device)
+            self.engine.load_state_dict(state_dict)
+            self.select = PercentileSelect(self.device)
+        self._plan_key = None
+        self.last = {}
+
+    # ---------------------------------------------------------------- static plan for a volume shape
+    def plan(self, size):
+        key = tuple(size)
+        if self._plan_key == key:
+            return self._plan
+        geo = dice_geometry(size, self.roi, self.overlap, self.border)
+        cube_ranges = sharding.balanced_ranges(geo.n_cubes, self.world)
+        slab_ranges = sharding.balanced_ranges(geo.padded[0], self.world)
+        c0, c1 = cube_ranges[self.rank]
+        p = dict(geo=geo, cube_ranges=cube_ranges, slab_ranges=slab_ranges, cubes=(c0, c1),
+                 in_planes=sharding.input_plane_range(geo, c0, c1), slab=slab_ranges[self.rank])
+        if self.world > 1:
+            p["pieces"] = sharding.plan_pieces(geo, cube_ranges, slab_ranges)
+            off, z0, _, total = sharding.piece_tables(geo, p["pieces"], self.rank, self.device)
+            p["piece_off"], p["piece_z0"], p["recv_total"] = off, z0, total
+        else:
+            r3 = self.roi ** 3
+            p["piece_off"] = torch.arange(geo.n_cubes, dtype=torch.int64, device=self.device) * r3
+            p["piece_z0"] = torch.zeros(geo.n_cubes, dtype=torch.int32, device=self.device)
+        s0, s1 = p["slab"]
+        p["out_planes"] = (min(s0, geo.size[0]), min(s1, geo.size[0]))   # un-padded part of this rank's slab
+        self._plan_key, self._plan = key, p
+        return p
+
+    # ---------------------------------------------------------------- stages (all async on the current stream)
+    def upload(self, volume_host: torch.Tensor, plan):
+        """volume_host: uint16 (Z,Y,X) host tensor (pinned for async copies).  Only this rank's planes move."""
+        z0, z1 = plan["in_planes"]
+        return volume_host[z0:z1].to(self.device, non_blocking=True), z0
+
+    def infer_cubes(self, vol_dev, vol_z0, plan, queue=None):
+        geo = plan["geo"]
+        c0, c1 = plan["cubes"]
+        r, e = self.roi, geo.edge
+        if queue is None:
+            queue = torch.empty((c1 - c0, r, r, r), dtype=torch.float32, device=self.device)
+        nbmax = min(self.batch, max(c1 - c0, 1))
+        xbuf = torch.empty((nbmax, e, e, e), dtype=torch.float32, device=self.device)
+        for b0 in range(c0, c1, nbmax):
+            nb = min(nbmax, c1 - b0)
+            x = dice_extract(vol_dev, vol_z0, geo, b0, nb, out=xbuf[:nb])
+            self.engine.forward(x, crop=self.border, out=queue[b0 - c0:b0 - c0 + nb], nb_cap=nbmax)
+        return queue
+
+    def assemble(self, queue, plan):
+        geo = plan["geo"]
+        if self.world > 1:
+            pieces = sharding.exchange_pieces(queue, plan["cubes"][0], geo, plan["pieces"], self.rank, self.group)
+        else:
+            pieces = queue.view(-1)
+        s0, s1 = plan["slab"]
+        vis = blend_gather(pieces, plan["piece_off"], plan["piece_z0"], geo, s0, s1 - s0)
+        norm3 = None
+        if self.normalize_intensity:
+            n_total = geo.padded[0] * geo.padded[1] * geo.padded[2]
+            norm3, self.last["percentiles"] = self.select.run(vis, n_total, self.sat_level, self.group,
+                                                              distributed=self.world > 1)
+        o0, o1 = plan["out_planes"]
+        return rescale_u16_crop(vis, s0, geo, norm3, o0, o1 - o0)
+
+    # ---------------------------------------------------------------- public API
+    def run_device(self, vol_dev, vol_z0, size):
+        """Inputs already in HBM -> this rank's uint16 output planes in HBM."""
+        with torch.cuda.device(self.device):
+            plan = self.plan(size)
+            queue = self.infer_cubes(vol_dev, vol_z0, plan)
+            return self.assemble(queue, plan)
+
+    def run(self, volume, out_host: torch.Tensor = None):
+        """volume: uint16 (Z,Y,X) numpy array or host tensor.  Returns (planes, (z_begin, z_end)): this rank's
+        slab of the assembled uint16 volume as a host numpy array (the whole volume when not sharded)."""
+        if isinstance(volume, np.ndarray):
+            volume = torch.from_numpy(volume)
+        if volume.dtype != torch.uint16 or volume.dim() != 3:
+            raise NeuroclearError("DicedInference.run expects a (Z,Y,X) uint16 volume")
+        with torch.cuda.device(self.device):
+            plan = self.plan(tuple(volume.shape))
+            vol_dev, z0 = self.upload(volume, plan)
+            out_dev = self.run_device(vol_dev, z0, tuple(volume.shape))
+            if out_host is None:
+                out_host = torch.empty(out_dev.shape, dtype=torch.uint16, pin_memory=True)
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_host.numpy(), plan["out_planes"]

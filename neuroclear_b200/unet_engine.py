@@ -1,0 +1,186 @@
+"""Execution plan of Unet_deconv.forward (reference models/networks.py:512-538) on the C ABI.
+
+Data layout in HBM (per batch of NB cubes of D x H x W voxels, L0 = full, L1 = /2, L2 = /4 resolution):
+
+    x      fp32 (NB, L0)            dice output / network input
+    raw0   fp32 (NB, L0, 64)        raw conv output of U1, U2, U12 (reused, consumed before rewritten)
+    a1     bf16 (NB, L0, 64)        IN+ReLU(U1)
+    cat1   bf16 (NB, L0, 128)       [IN+ReLU(U2) | t_conv1]          = torch.cat([conv1, t_conv1], 1)
+    p1     bf16 (NB, L1, 64)        maxpool1
+    raw1   fp32 (NB, L1, 128)       raw output of U3, U4, U9, U10
+    a3     bf16 (NB, L1, 128)       IN+ReLU(U3) / (U9) / (U10)
+    cat2   bf16 (NB, L1, 256)       [IN+ReLU(U4) | t_conv2]          = torch.cat([conv2, t_conv2], 1)
+    p2     bf16 (NB, L2, 128)       maxpool2
+    raw2   fp32 (NB, L2, 256)       raw output of U5, U6, U7
+    b1,b2  bf16 (NB, L2, 256)       bottom-layer ping-pong
+    y      fp32 (NB, L0 - 2*crop)   sigmoid output, border already cut
+
+All activations are NDHWC; the concat buffers make torch.cat a no-op (producers write channel slices).
+Conv biases in front of InstanceNorm(affine=False) cancel exactly in the mean subtraction and are not applied.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, i32, i64, ptr, stream_ptr
+
+IN_EPS = 1e-5  # torch.nn.InstanceNorm3d default, used by networks.get_norm_layer (networks.py:33-34)
+
+_K3_LAYERS = [  # (state_dict prefix, Cin, Cout)
+    ("double_conv1.convolution.3", 64, 64),
+    ("double_conv2.convolution.0", 64, 128),
+    ("double_conv2.convolution.3", 128, 128),
+    ("bottom_layer.convolution.0", 128, 256),
+    ("bottom_layer.convolution.3", 256, 256),
+    ("bottom_layer.convolution.6", 256, 256),
+    ("ex_double_conv2.convolution.0", 256, 128),
+    ("ex_double_conv2.convolution.3", 128, 128),
+    ("ex_conv1_1.convolution.0", 128, 64),
+]
+_CT_LAYERS = [("t_conv2", 256, 128), ("t_conv1", 128, 64)]
+
+# 2 * MACs of the 14 convolutions per network-input voxel: 3 642 983 792 000 per 140^3 cube
+FLOP_PER_VOXEL = 1_327_618
+
+
+class UnetDeconvEngine:
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.NeuroclearError("UnetDeconvEngine needs a CUDA device (no CPU fallback)")
+        _lib.load()
+        self.packed = {}
+        self.bias = {}
+        self.w_first = None
+        self.head = None
+        self._ws_key = None
+        self._ws = None
+        #: when set to a list, forward() brackets every tensor-core conv launch with CUDA events on the launching
+        #: stream and appends (layer, flops, start_event, end_event) — bench.py's live roofline measurement
+        self.profile = None
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd):
+        dev = self.device
+        f = lambda k: sd[k].detach().to(dev, torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            self.w_first = f("double_conv1.convolution.0.weight").reshape(64, 27).contiguous()
+            for prefix, cin, cout in _K3_LAYERS:
+                w = f(prefix + ".weight")
+                assert tuple(w.shape) == (cout, cin, 3, 3, 3), (prefix, tuple(w.shape))
+                out = torch.empty(_lib.load().nc_packed_weight_bytes(cout, cin, 0), dtype=torch.uint8, device=dev)
+                call("nc_pack_weights_conv3d_k3", ptr(w), cout, cin, ptr(out), stream_ptr())
+                self.packed[prefix] = out
+            for prefix, cin, cout in _CT_LAYERS:
+                w = f(prefix + ".weight")
+                assert tuple(w.shape) == (cin, cout, 2, 2, 2), (prefix, tuple(w.shape))
+                out = torch.empty(_lib.load().nc_packed_weight_bytes(cout, cin, 1), dtype=torch.uint8, device=dev)
+                call("nc_pack_weights_convT3d_k2s2", ptr(w), cin, cout, ptr(out), stream_ptr())
+                self.packed[prefix] = out
+                self.bias[prefix] = f(prefix + ".bias")
+            self.head = torch.cat([f("one_by_one.weight").reshape(64), f("one_by_one.bias").reshape(1),
+                                   f("one_by_one_2.weight").reshape(1), f("one_by_one_2.bias").reshape(1)]).contiguous()
+            torch.cuda.current_stream().synchronize()  # the fp32 staging copies die here
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, nb, d, h, w):
+        key = (nb, d, h, w)
+        if self._ws_key == key:
+            return self._ws
+        self._ws = None  # release before allocating the new one
+        dev = self.device
+        l0, l1, l2 = d * h * w, (d // 2) * (h // 2) * (w // 2), (d // 4) * (h // 4) * (w // 4)
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda n, dt: torch.empty(n, dtype=dt, device=dev)
+        lib = _lib.load()
+        rows = max(
+            lib.nc_conv3d_k3_stats_rows(1, nb, d, h, w, 64) * 64,
+            lib.nc_conv3d_k3_stats_rows(64, nb, d, h, w, 64) * 64,
+            lib.nc_conv3d_k3_stats_rows(64, nb, d // 2, h // 2, w // 2, 128) * 128,
+            lib.nc_conv3d_k3_stats_rows(128, nb, d // 4, h // 4, w // 4, 256) * 256,
+        )
+        ws = dict(
+            raw0=e(nb * l0 * 64, f32), a1=e(nb * l0 * 64, bf), cat1=e(nb * l0 * 128, bf), p1=e(nb * l1 * 64, bf),
+            raw1=e(nb * l1 * 128, f32), a3=e(nb * l1 * 128, bf), cat2=e(nb * l1 * 256, bf), p2=e(nb * l2 * 128, bf),
+            raw2=e(nb * l2 * 256, f32), b1=e(nb * l2 * 256, bf), b2=e(nb * l2 * 256, bf),
+            stats=e(rows * 2, f32), mr=e(nb * 2 * 256, f32),
+        )
+        self._ws_key, self._ws = key, ws
+        return ws
+
+    def workspace_bytes(self, nb, d, h, w):
+        ws = self._workspace(nb, d, h, w)
+        return sum(t.numel() * t.element_size() for t in ws.values())
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, crop: int = 0, out=None, nb_cap=None):
+        """x: float32 CUDA (NB, D, H, W) contiguous, D,H,W % 4 == 0 -> float32 (NB, D-2c, H-2c, W-2c)."""
+        if self.head is None:
+            raise _lib.NeuroclearError("UnetDeconvEngine: weights not loaded")
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4):
+            raise _lib.NeuroclearError("UnetDeconvEngine.forward: x must be a contiguous float32 CUDA (NB,D,H,W) tensor")
+        nb, d, h, w = x.shape
+        if d % 4 or h % 4 or w % 4:
+            raise _lib.NeuroclearError("Unet_deconv needs D, H, W divisible by 4 (two 2x poolings + concat)")
+        ws = self._workspace(max(nb, nb_cap or 0), d, h, w)
+        if out is None:
+            out = torch.empty((nb, d - 2 * crop, h - 2 * crop, w - 2 * crop), dtype=torch.float32, device=x.device)
+        s = stream_ptr()
+        lib = _lib.load()
+        d1, h1, w1, d2, h2, w2 = d // 2, h // 2, w // 2, d // 4, h // 4, w // 4
+        st, mr = ws["stats"], ws["mr"]
+
+        def stats(cin, dd, hh, ww, c):
+            rows = lib.nc_conv3d_k3_stats_rows(cin, nb, dd, hh, ww, c)
+            call("nc_in_stats_finalize", ptr(st), nb, i64(rows // nb), c, i64(dd * hh * ww), IN_EPS, ptr(mr), s)
+
+        def conv(prefix, src, dd, hh, ww, cin, cout, raw):
+            if self.profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            call("nc_conv3d_k3_fwd", ptr(src), nb, dd, hh, ww, cin, ptr(self.packed[prefix]), cout, ptr(raw), ptr(st), s)
+            if self.profile is not None:
+                e1.record()
+                self.profile.append((prefix, 2.0 * nb * dd * hh * ww * cout * cin * 27, e0, e1))
+            stats(cin, dd, hh, ww, cout)
+
+        def apply(raw, dd, hh, ww, c, dst, ld, coff, pooled=None):
+            call("nc_in_relu_apply", ptr(raw), ptr(mr), nb, dd, hh, ww, c, ptr(dst), ld, coff, ptr(pooled), s)
+
+        # ---- level 0 down
+        call("nc_conv3d_cin1_k3_fwd", ptr(x), ptr(self.w_first), nb, d, h, w, 64, ptr(ws["raw0"]), ptr(st), s)
+        stats(1, d, h, w, 64)
+        apply(ws["raw0"], d, h, w, 64, ws["a1"], 64, 0)
+        conv("double_conv1.convolution.3", ws["a1"], d, h, w, 64, 64, ws["raw0"])
+        apply(ws["raw0"], d, h, w, 64, ws["cat1"], 128, 0, ws["p1"])                      # conv1 | maxpool1
+        # ---- level 1 down
+        conv("double_conv2.convolution.0", ws["p1"], d1, h1, w1, 64, 128, ws["raw1"])
+        apply(ws["raw1"], d1, h1, w1, 128, ws["a3"], 128, 0)
+        conv("double_conv2.convolution.3", ws["a3"], d1, h1, w1, 128, 128, ws["raw1"])
+        apply(ws["raw1"], d1, h1, w1, 128, ws["cat2"], 256, 0, ws["p2"])                  # conv2 | maxpool2
+        # ---- bottom
+        conv("bottom_layer.convolution.0", ws["p2"], d2, h2, w2, 128, 256, ws["raw2"])
+        apply(ws["raw2"], d2, h2, w2, 256, ws["b1"], 256, 0)
+        conv("bottom_layer.convolution.3", ws["b1"], d2, h2, w2, 256, 256, ws["raw2"])
+        apply(ws["raw2"], d2, h2, w2, 256, ws["b2"], 256, 0)
+        conv("bottom_layer.convolution.6", ws["b2"], d2, h2, w2, 256, 256, ws["raw2"])
+        apply(ws["raw2"], d2, h2, w2, 256, ws["b1"], 256, 0)
+        # ---- level 1 up: cat2 = [conv2 | t_conv2]
+        call("nc_convT3d_k2s2_fwd", ptr(ws["b1"]), nb, d2, h2, w2, 256, ptr(self.packed["t_conv2"]),
+             ptr(self.bias["t_conv2"]), 128, ptr(ws["cat2"]), 256, 128, s)
+        conv("ex_double_conv2.convolution.0", ws["cat2"], d1, h1, w1, 256, 128, ws["raw1"])
+        apply(ws["raw1"], d1, h1, w1, 128, ws["a3"], 128, 0)
+        conv("ex_double_conv2.convolution.3", ws["a3"], d1, h1, w1, 128, 128, ws["raw1"])
+        apply(ws["raw1"], d1, h1, w1, 128, ws["a3"], 128, 0)
+        # ---- level 0 up: cat1 = [conv1 | t_conv1]
+        call("nc_convT3d_k2s2_fwd", ptr(ws["a3"]), nb, d1, h1, w1, 128, ptr(self.packed["t_conv1"]),
+             ptr(self.bias["t_conv1"]), 64, ptr(ws["cat1"]), 128, 64, s)
+        conv("ex_conv1_1.convolution.0", ws["cat1"], d, h, w, 128, 64, ws["raw0"])
+        # ---- head: IN + ReLU + 1x1x1 + 1x1x1 + sigmoid (+ border cut)
+        call("nc_head_1x1_sigmoid_fwd", ptr(ws["raw0"]), ptr(mr), ptr(self.head), nb, d, h, w, 64, crop, ptr(out), s)
+        return out
+
+    #: kernels launched by one forward() (for bench.py's gpu_launches): 1 + 9 convs, 2 convT, 10 finalize,
+    #: 9 apply, 1 head
+    LAUNCHES_PER_FORWARD = 1 + 9 + 2 + 10 + 9 + 1

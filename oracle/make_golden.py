@@ -61,13 +61,14 @@ def golden_dice_assemble():
     vol = rng.integers(0, 65536, size, dtype=np.uint16)
     g = geometry.dice_geometry(size, roi, ov, bc)
     out = {}
+    e = g.edge
+    fake = rng.random((g.n_cubes, 1, e, e, e), dtype=np.float32)                     # stand-in network outputs
     for normalize in (True, False):
         ds, asm, _ = _ref_dataset_and_assembler(vol, roi, ov, bc, normalize)
         cubes = np.stack([ds[i]["A"].numpy() for i in range(len(ds))])             # (n,1,E,E,E) float32
         dd = dice.DirectDicer(vol, g)
         for i in range(g.n_cubes):
             assert np.array_equal(cubes[i], dd.cube(i)) and np.array_equal(cubes[i], dice.dice_cube_gather(vol, g, i))
-        fake = rng.random(cubes.shape, dtype=np.float32)                             # stand-in network outputs
         with redirect_stdout(io.StringIO()):
             for i in range(g.n_cubes):
                 t = torch.from_numpy(fake[i][None])
@@ -89,21 +90,21 @@ def golden_dice_assemble():
 
 
 def golden_unet():
-    """Reference Unet_deconv (networks.define_G) vs oracle on a 16^3 and a 24x16x20 input, shared state_dict."""
+    """Reference Unet_deconv (networks.define_G) vs oracle on a 16^3 and a 24x16x20 input.  The weights are
+    oracle.unet.random_state_dict(seed=0, bias_std=0.1) loaded into the reference module (7 M parameters are
+    regenerated from the seed in the tests instead of being committed; a checksum guards against RNG drift)."""
     rh.install()
     from models import networks
-    torch.manual_seed(0)
-    net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
     net.eval()
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    assert {k: tuple(v.shape) for k, v in sd.items()} == unet.STATE_DICT_SHAPES
-    assert sum(v.numel() for v in sd.values()) == unet.N_PARAMS
-    # biases are zero at init; perturb them so bias handling is covered
-    g = torch.Generator().manual_seed(1)
-    for k in sd:
-        if k.endswith("bias"):
-            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+    ref_sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in ref_sd.items()} == unet.STATE_DICT_SHAPES
+    assert list(ref_sd.keys()) == list(unet.STATE_DICT_SHAPES.keys())
+    assert sum(v.numel() for v in ref_sd.values()) == unet.N_PARAMS
+    sd = unet.random_state_dict(seed=0, bias_std=0.1)
     net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(1)
     out = {}
     for name, shape in (("a", (1, 1, 16, 16, 16)), ("b", (1, 1, 24, 16, 20))):
         x = torch.rand(shape, generator=g)
@@ -113,10 +114,7 @@ def golden_unet():
         err = (y_ref - y_or).abs().max().item()
         assert err <= 1e-6, err
         out["x_" + name], out["y_" + name] = x.numpy(), y_ref.numpy()
-    # weights are regenerated from the seed in the test; store a checksum and a few slices instead of 28 MB
-    out["w_checksum"] = np.array([float(sum(v.double().sum() for v in sd.values())),
-                                  float(sum(v.double().abs().sum() for v in sd.values()))])
-    torch.save(sd, os.path.join(GOLD, "_unet_state_dict.pt"))   # git-ignored helper (28 MB); see below
+    out["w_checksum"] = np.array(unet.state_dict_checksum(sd))
     np.savez_compressed(os.path.join(GOLD, "unet_small.npz"), **out)
 
 

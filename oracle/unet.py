@@ -31,13 +31,14 @@ STATE_DICT_SHAPES = {
 N_PARAMS = 7_077_251  # README screenshot "7.077 M"; SURVEY.md §4
 
 
-def random_state_dict(seed: int = 0) -> dict:
-    """Kaiming fan_in normal weights / zero bias like networks.init_weights('kaiming') (networks.py:88-119)."""
+def random_state_dict(seed: int = 0, bias_std: float = 0.0) -> dict:
+    """Kaiming fan_in normal weights like networks.init_weights('kaiming') (networks.py:88-119); biases are zero
+    as in the reference's init unless bias_std > 0 (used by the fixtures so that bias handling is exercised)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for k, shape in STATE_DICT_SHAPES.items():
         if k.endswith("bias"):
-            sd[k] = torch.zeros(shape)
+            sd[k] = torch.randn(shape, generator=g) * bias_std if bias_std > 0 else torch.zeros(shape)
         else:
             fan_in = shape[1] * shape[2] * shape[3] * shape[4]   # torch fan_in: size(1) * receptive field
             sd[k] = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
@@ -48,6 +49,10 @@ def _conv_in_relu(x, sd, prefix):
     x = F.conv3d(x, sd[prefix + ".weight"], sd[prefix + ".bias"], stride=1, padding=1)
     x = F.instance_norm(x, eps=1e-5)          # InstanceNorm3d(affine=False, track_running_stats=False)
     return F.relu(x)
+
+
+def state_dict_checksum(sd: dict):
+    return [float(sum(v.double().sum() for v in sd.values())), float(sum(v.double().abs().sum() for v in sd.values()))]
 
 
 def unet_deconv_forward(x: torch.Tensor, sd: dict, taps: dict | None = None) -> torch.Tensor:

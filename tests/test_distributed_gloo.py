@@ -1,0 +1,82 @@
+"""CPU, world_size 2 over gloo: the one exchange step of the sharded path (pieces of cube outputs to the z-slab
+owners) plus the histogram all-reduce, checked against the oracle's sequential blend of ALL cubes."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import assemble, geometry as ogeo
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cube_output(geo, index):
+    rng = np.random.default_rng(1000 + index)
+    return rng.random((geo.roi,) * 3, dtype=np.float32)
+
+
+def _blend_from_pieces(recv, off, z0, geo, s0, s1):
+    """numpy statement of nc_blend_gather_f32's contract on the received pieces."""
+    r, st = geo.roi, geo.step
+    out = np.zeros((s1 - s0, geo.padded[1], geo.padded[2]), dtype=np.float32)
+    cnt = np.zeros_like(out)
+    for cube in range(geo.n_cubes):                       # ascending cube index = reference order
+        if off[cube] < 0:
+            continue
+        oz, oy, ox = geo.origin(cube)
+        a, b = max(oz, s0), min(oz + r, s1)
+        if a >= b:
+            continue
+        n_planes = b - a
+        piece = recv[off[cube]: off[cube] + n_planes * r * r].reshape(n_planes, r, r)
+        assert a - oz == z0[cube]
+        out[a - s0:b - s0, oy:oy + r, ox:ox + r] += piece / 8
+        cnt[a - s0:b - s0, oy:oy + r, ox:ox + r] += 1
+    return (out / cnt) * 8
+
+
+def _worker(rank, world, port, size, roi, ov, bc, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neuroclear_b200 import sharding
+        geo = ogeo.dice_geometry(size, roi, ov, bc)
+        cubes = sharding.balanced_ranges(geo.n_cubes, world)
+        slabs = sharding.balanced_ranges(geo.padded[0], world)
+        plan = sharding.plan_pieces(geo, cubes, slabs)
+        c0, c1 = cubes[rank]
+        queue = torch.from_numpy(np.stack([_cube_output(geo, i) for i in range(c0, c1)]))
+        recv = sharding.exchange_pieces(queue, c0, geo, plan, rank)
+        off, z0, sizes, total = sharding.piece_tables(geo, plan, rank, "cpu")
+        assert recv.numel() == total
+        s0, s1 = slabs[rank]
+        mine = _blend_from_pieces(recv.numpy(), off.numpy(), z0.numpy(), geo, s0, s1)
+        full, _ = assemble.blend_sequential([_cube_output(geo, i) for i in range(geo.n_cubes)], geo)
+        assert np.array_equal(mine, full[s0:s1]), "sharded blend differs from the sequential reference order"
+        # histogram all-reduce used by the percentile select
+        hist = torch.bincount(torch.from_numpy((mine.reshape(-1) * 15).astype(np.int64)), minlength=16)
+        dist.all_reduce(hist)
+        ref = np.bincount((full.reshape(-1) * 15).astype(np.int64), minlength=16)
+        assert np.array_equal(hist.numpy(), ref)
+        open(os.path.join(result_dir, "ok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_and_blend(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), (31, 40, 27), 12, 3, 2, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def test_three_rank_uneven(tmp_path):
+    world = 3
+    mp.spawn(_worker, args=(world, _free_port(), (50, 20, 33), 16, 4, 1, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))

@@ -1,0 +1,128 @@
+"""CPU: the C-ABI library loads and exports everything the header declares; host-side integer logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import geometry as ogeo
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "neuroclear_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nc_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    from neuroclear_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and header disagree"
+    assert lib.nc_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU every compute path must fail loudly instead of computing on the host."""
+    from neuroclear_b200 import _lib, networks
+    from neuroclear_b200.unet_engine import UnetDeconvEngine
+    with pytest.raises(_lib.NeuroclearError):
+        UnetDeconvEngine("cpu")
+    import io
+    from contextlib import redirect_stdout
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
+    with torch.no_grad(), pytest.raises(_lib.NeuroclearError):
+        net(torch.zeros(1, 1, 8, 8, 8))
+
+
+def test_define_g_state_dict_is_the_references():
+    import io
+    from contextlib import redirect_stdout
+    from neuroclear_b200 import networks
+    from oracle import unet
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(unet.STATE_DICT_SHAPES.keys())
+    assert {k: tuple(v.shape) for k, v in sd.items()} == unet.STATE_DICT_SHAPES
+    assert sum(p.numel() for p in net.parameters()) == 7_077_251
+    assert all(float(v.abs().sum()) == 0.0 for k, v in sd.items() if k.endswith("bias"))   # init_weights zeroes biases
+    net.load_state_dict(unet.random_state_dict(0))                                          # reference checkpoints load
+    with pytest.raises(NotImplementedError):
+        networks.define_G(1, 1, 64, "resnet_9blocks", "instance")
+
+
+@pytest.mark.parametrize("size,roi,ov", [((128, 128, 128), 120, 15), ((900, 900, 900), 120, 15),
+                                         ((1024, 2048, 2048), 120, 15), ((31, 40, 27), 12, 3), ((1, 1, 1), 8, 2),
+                                         ((105, 210, 119), 120, 15)])
+def test_c_geometry_matches_oracle(lib, size, roi, ov):
+    from neuroclear_b200.dicing import dice_geometry
+    g, o = dice_geometry(size, roi, ov, 1), ogeo.dice_geometry(size, roi, ov, 1)
+    assert (g.padded, g.steps, g.n_cubes) == (o.padded, o.steps, o.n_cubes)
+    assert all(p > n for p, n in zip(g.padded, g.size))          # pad is always >= 1 (util/util.py:207-209)
+
+
+def test_c_geometry_rejects_bad_arguments(lib):
+    from neuroclear_b200 import _lib
+    from neuroclear_b200.dicing import dice_geometry
+    with pytest.raises(_lib.NeuroclearError):
+        dice_geometry((10, 10, 10), 8, 8, 1)
+    with pytest.raises(_lib.NeuroclearError):
+        dice_geometry((10, 0, 10), 8, 2, 1)
+
+
+@pytest.mark.parametrize("n", [2, 7, 1000, 39 * 48 * 39, 884_736_000])
+def test_percentile_rank_arithmetic_matches_numpy(n):
+    from neuroclear_b200.dicing import percentile_ranks
+    ranks, t_lo, t_hi = percentile_ranks(n, (0.25, 99.75))
+    if n <= 100_000:
+        rng = np.random.default_rng(n)
+        a = rng.random(n, dtype=np.float32)
+        s = np.sort(a)
+
+        def lerp(lo, hi, t):   # numpy _lerp with float32 order statistics and float64 gamma
+            diff = np.float32(s[hi] - s[lo])
+            r = np.float64(s[lo]) + np.float64(diff) * t
+            return np.float64(s[hi]) - np.float64(diff) * (1 - t) if t >= 0.5 else r
+        mine = (lerp(ranks[0], ranks[1], t_lo), lerp(ranks[2], ranks[3], t_hi))
+        ref = np.percentile(a, (0.25, 99.75))
+        assert ref.dtype == np.float64 and mine[0] == ref[0] and mine[1] == ref[1]
+    assert 0 <= ranks[0] <= ranks[1] < n and ranks[2] <= ranks[3] < n
+
+
+def test_sharding_plans_cover_everything():
+    from neuroclear_b200 import sharding
+    for size, world in [((900, 900, 900), 8), ((128, 128, 128), 2), ((31, 40, 27), 3), ((1024, 2048, 2048), 8)]:
+        roi, ov, bc = (12, 3, 2) if size[0] < 100 else (120, 15, 10)
+        g = ogeo.dice_geometry(size, roi, ov, bc)
+        cubes = sharding.balanced_ranges(g.n_cubes, world)
+        slabs = sharding.balanced_ranges(g.padded[0], world)
+        assert cubes[0][0] == 0 and cubes[-1][1] == g.n_cubes and all(a[1] == b[0] for a, b in zip(cubes, cubes[1:]))
+        assert max(c1 - c0 for c0, c1 in cubes) - min(c1 - c0 for c0, c1 in cubes) <= 1
+        plan = sharding.plan_pieces(g, cubes, slabs)
+        # every plane of every cube lands on exactly one slab owner
+        planes = np.zeros((g.n_cubes, roi), dtype=np.int32)
+        for src in range(world):
+            for dst in range(world):
+                for pc in plan[src][dst]:
+                    assert cubes[src][0] <= pc.cube < cubes[src][1]
+                    z0, _ = sharding.cube_z_extent(g, pc.cube)
+                    assert slabs[dst][0] <= z0 + pc.p0 and z0 + pc.p1 <= slabs[dst][1]
+                    planes[pc.cube, pc.p0:pc.p1] += 1
+        assert (planes == 1).all()
+        # input plane ranges contain everything reflect indexing can touch
+        for c0, c1 in cubes:
+            lo, hi = sharding.input_plane_range(g, c0, c1)
+            for cube in (c0, c1 - 1):
+                oz = g.origin(cube)[0]
+                j = np.arange(oz - bc, oz - bc + g.edge)
+                j = np.where(j < 0, -j, j)
+                j = np.where(j >= g.padded[0], 2 * (g.padded[0] - 1) - j, j)
+                j = j[j < size[0]]
+                assert j.size == 0 or (lo <= j.min() and j.max() < hi)

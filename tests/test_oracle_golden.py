@@ -1,0 +1,96 @@
+"""CPU: the oracle against the fixtures the REFERENCE produced (tests/golden, written by oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+from oracle import assemble, dice, geometry, mip, unet
+
+
+def test_geometry_kats():
+    rows = np.load(os.path.join(GOLDEN, "geometry.npz"))["rows"]
+    for row in rows:
+        size, (roi, ov, bc), padded, steps = tuple(row[:3]), row[3:6], tuple(row[6:9]), tuple(row[9:12])
+        g = geometry.dice_geometry(size, int(roi), int(ov), int(bc))
+        assert g.padded == padded and g.steps == steps
+    # SURVEY.md §4 known answers
+    g = geometry.dice_geometry((900, 900, 900), 120, 15, 10)
+    assert g.padded == (960, 960, 960) and g.steps == (9, 9, 9) and g.n_cubes == 729
+    g = geometry.dice_geometry((128, 128, 128), 120, 15, 10)
+    assert g.padded == (225, 225, 225) and g.steps == (2, 2, 2) and g.edge == 140
+    g = geometry.dice_geometry((1024, 2048, 2048), 120, 15, 10)
+    assert g.padded == (1065, 2115, 2115) and g.steps == (10, 20, 20) and g.n_cubes == 4000
+
+
+def test_cube_order_x_fastest():
+    g = geometry.dice_geometry((31, 40, 27), 12, 3, 2)
+    assert g.index_to_cube(0) == (0, 0, 0) and g.index_to_cube(1) == (0, 0, 1)
+    assert g.index_to_cube(g.steps[2]) == (0, 1, 0) and g.index_to_cube(g.steps[2] * g.steps[1]) == (1, 0, 0)
+
+
+def _fixture():
+    return np.load(os.path.join(GOLDEN, "dice_assemble_31x40x27.npz"))
+
+
+def test_dice_matches_reference_cubes():
+    f = _fixture()
+    roi, ov, bc = (int(v) for v in f["params"])
+    vol = f["volume"]
+    g = geometry.dice_geometry(vol.shape, roi, ov, bc)
+    dd = dice.DirectDicer(vol, g)
+    for i in range(g.n_cubes):
+        assert np.array_equal(f["cubes"][i], dd.cube(i))
+        assert np.array_equal(f["cubes"][i], dice.dice_cube_gather(vol, g, i))
+
+
+def test_u16_normalise_is_fp32_divide():
+    v = np.arange(65536, dtype=np.uint16)
+    ref = torch.from_numpy((v / (2 ** 16 * 1.0 - 1)).astype(float)).float().numpy()   # base_dataset.py:134-143,291-295
+    assert np.array_equal(ref, v.astype(np.float32) / np.float32(65535.0))
+
+
+def test_assemble_matches_reference():
+    f = _fixture()
+    roi, ov, bc = (int(v) for v in f["params"])
+    g = geometry.dice_geometry(f["volume"].shape, roi, ov, bc)
+    cubes = [assemble.crop_border(c, bc) for c in f["fake"]]
+    vis, mask = assemble.blend_sequential(cubes, g)
+    assert np.array_equal(vis, f["blend"])
+    assert np.array_equal(mask, assemble.analytic_count(g)) and mask.max() == 8.0
+    plain, _ = assemble.finish(vis, g, False)
+    assert plain.dtype == np.uint16 and np.array_equal(plain, f["final_plain"])
+    norm, pcts = assemble.finish(vis, g, True)
+    assert np.array_equal(norm, f["final_norm"]) and np.allclose(pcts, f["pcts"], rtol=0, atol=0)
+
+
+def test_identity_roundtrip_one_lsb():
+    """uint16 -> dice -> (identity network) -> assemble -> uint16 differs by at most 1 LSB."""
+    rng = np.random.default_rng(1)
+    vol = rng.integers(0, 65536, (20, 33, 25), dtype=np.uint16)
+    g = geometry.dice_geometry(vol.shape, 12, 3, 2)
+    outs = [dice.dice_cube_gather(vol, g, i) for i in range(g.n_cubes)]
+    final, _ = assemble.assemble(outs, g, False)
+    assert final.shape == vol.shape
+    assert np.abs(final.astype(np.int64) - vol.astype(np.int64)).max() <= 1
+
+
+def test_unet_matches_reference_module():
+    f = np.load(os.path.join(GOLDEN, "unet_small.npz"))
+    sd = unet.random_state_dict(seed=0, bias_std=0.1)
+    assert np.allclose(unet.state_dict_checksum(sd), f["w_checksum"], rtol=1e-12), "torch RNG drift: regenerate golden"
+    assert sum(v.numel() for v in sd.values()) == unet.N_PARAMS == 7_077_251
+    for name in "ab":
+        y = unet.unet_deconv_forward(torch.from_numpy(f["x_" + name]), sd).numpy()
+        assert np.abs(y - f["y_" + name]).max() <= 1e-5
+
+
+def test_mip_matches_reference():
+    f = np.load(os.path.join(GOLDEN, "mip_12.npz"))
+    vol = torch.from_numpy(f["vol"])
+    np.random.seed(5)
+    state = np.random.get_state()
+    for axis in range(3):
+        np.random.set_state(state)
+        proj, start = mip.get_projection(vol, 4, axis)
+        assert start == int(f[f"start{axis}"]) and np.array_equal(proj.numpy(), f[f"proj{axis}"])
