@@ -10,7 +10,7 @@
  *     tensor's data_ptr()); nothing here allocates persistent device memory.
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, one host thread per
  *     device; return value 0 = OK, negative = error with the message in nc_last_error() (thread-local).
- *   - activations between the tensor-core convolutions are bf16, NDHWC ("channels-last-3d"); convolution
+ *   - activations between the tensor-core convolutions are fp16, NDHWC ("channels-last-3d"); convolution
  *     outputs that feed InstanceNorm are raw fp32 NDHWC plus per-tile statistics partials.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with an error.
  */
@@ -63,23 +63,23 @@ int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d,
                           float* y_raw, float* stats_partial, nc_stream_t stream);
 
 /* Packed weight sizes / packing for the tensor-core kernels.  conv: w is OIDHW float32 (Cout,Cin,3,3,3);
- * convT: w is IODHW float32 (Cin,Cout,2,2,2) (torch ConvTranspose3d layout).  Output is the bf16 swizzled
+ * convT: w is IODHW float32 (Cin,Cout,2,2,2) (torch ConvTranspose3d layout).  Output is the fp16 swizzled
  * shared-memory image the kernels stream with bulk copies. */
 int64_t nc_packed_weight_bytes(int32_t cout, int32_t cin, int32_t transposed);
 int nc_pack_weights_conv3d_k3(const float* w_oidhw, int32_t cout, int32_t cin, void* packed, nc_stream_t stream);
 int nc_pack_weights_convT3d_k2s2(const float* w_iodhw, int32_t cin, int32_t cout, void* packed, nc_stream_t stream);
 
 /* nn.Conv3d(Cin -> Cout, k3 s1 p1) of double_conv / triple_conv / last_conv (networks.py:413-476): tcgen05
- * implicit GEMM, bf16 operands, fp32 accumulate.  x: bf16 NDHWC (NB,D,H,W,Cin) (Cin may be a concat buffer);
+ * implicit GEMM, fp16 operands, fp32 accumulate.  x: fp16 NDHWC (NB,D,H,W,Cin) (Cin may be a concat buffer);
  * y_raw: float32 NDHWC (NB,D,H,W,Cout) without bias; stats_partial as above.  Cin % 64 == 0, Cout in {64,128k}. */
-int nc_conv3d_k3_fwd(const void* x_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
+int nc_conv3d_k3_fwd(const void* x_f16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
                      int32_t cout, float* y_raw, float* stats_partial, nc_stream_t stream);
 
 /* nn.ConvTranspose3d(Cin -> Cout, k2 s2) t_conv2 / t_conv1 (networks.py:500,503) fused with the channel concat
- * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as bf16 into
+ * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as fp16 into
  * channels [y_coff, y_coff+Cout) of an NDHWC buffer (NB,2D,2H,2W,y_ld). */
-int nc_convT3d_k2s2_fwd(const void* x_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
-                        const void* packed, const float* bias, int32_t cout, void* y_bf16, int32_t y_ld,
+int nc_convT3d_k2s2_fwd(const void* x_f16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
+                        const void* packed, const float* bias, int32_t cout, void* y_f16, int32_t y_ld,
                         int32_t y_coff, nc_stream_t stream);
 
 /* InstanceNorm3d(affine=False, eps) statistics (networks.py:33-34): deterministic fixed-order reduction of the
@@ -88,10 +88,10 @@ int nc_in_stats_finalize(const float* stats_partial, int32_t nb, int64_t rows_pe
                          int64_t voxels_per_sample, float eps, float* mean_rstd, nc_stream_t stream);
 
 /* InstanceNorm apply + ReLU (+ MaxPool3d(2), networks.py:491,494) + write into a concat slice:
- * y[..., y_coff:y_coff+C] = bf16(relu((raw - mean) * rstd)); if pooled != NULL also the 2x2x2 max as bf16
+ * y[..., y_coff:y_coff+C] = fp16(relu((raw - mean) * rstd)); if pooled != NULL also the 2x2x2 max as fp16
  * NDHWC (NB,D/2,H/2,W/2,C).  raw: float32 NDHWC. */
 int nc_in_relu_apply(const float* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
-                     int32_t c, void* y_bf16, int32_t y_ld, int32_t y_coff, void* pooled_bf16, nc_stream_t stream);
+                     int32_t c, void* y_f16, int32_t y_ld, int32_t y_coff, void* pooled_f16, nc_stream_t stream);
 
 /* Tail of Unet_deconv.forward (networks.py:504-510,533-536): InstanceNorm+ReLU of ex_conv1_1, one_by_one (C->1),
  * one_by_one_2 (1->1) and sigmoid in one pass; optionally drops `crop` voxels per side (the border cut of

@@ -3,7 +3,7 @@
 // Replaces the torch.nn.Conv3d / ConvTranspose3d calls of Unet_deconv (reference models/networks.py:478-538,
 // layers U2..U12 of SURVEY.md §2c). Design (not a translation of any library kernel):
 //
-//   * activations are bf16 NDHWC; one GEMM row = one voxel, K = taps x Cin walked as (64-channel chunk, tap)
+//   * activations are fp16 NDHWC (fp16, not bf16: see DESIGN.md "Operand precision"); one GEMM row = one voxel, K = taps x Cin walked as (64-channel chunk, tap)
 //   * a CTA owns an output tile of 8(w) x 16(h) x TD(d) voxels = TD accumulators of 128 rows in TMEM
 //   * the input is staged ONCE per (tile, chunk) as TD+KS-1 halo planes of (8+KS-1) x (16+KS-1) voxels, each
 //     voxel one 128-byte row, written by a 5-D TMA box with SWIZZLE_128B (out-of-volume rows arrive as zeros
@@ -17,9 +17,9 @@
 //     tile i overlaps the MMAs of tile i+1. The grid is persistent (<= #SMs CTAs, static tile stride).
 //   * epilogue MODE 0: raw fp32 NDHWC store + per-tile per-channel (sum, sum of squares) partials taken from
 //     the fp32 accumulators (InstanceNorm statistics, reduced deterministically later);
-//     MODE 1: transposed-conv scatter (voxel (2d+a,2h+b,2w+c)), +bias, bf16 store into a channel slice of the
+//     MODE 1: transposed-conv scatter (voxel (2d+a,2h+b,2w+c)), +bias, fp16 store into a channel slice of the
 //     skip-concat buffer.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -67,7 +67,7 @@ struct ConvTcArgs {
   float* stats_partial;  // [spatial tile][2][ldo]
   int ldo;               // total output channels (row pitch of out_raw)
   // MODE 1
-  __nv_bfloat16* out_bf16;  // [NB][2D][2H][2W][ld1]
+  __half* out_f16;  // [NB][2D][2H][2W][ld1]
   const float* bias;
   int ld1, coff1, cout1;
   int desc_base_mode;  // 0: base_offset field = 0 (absolute-address swizzle); 1: (addr>>7)&7
@@ -92,6 +92,14 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcArgs& a, int tile, 
   t.h0 = ht * TH;
   t.d0 = dt * td;
   return t;
+}
+
+// fp32 pair -> packed fp16x2, saturating at the largest finite half instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
 }
 
 // Column sums over the 32 lanes of a warp for 32 per-lane values: afterwards lane l holds sum_lanes v[l].
@@ -207,7 +215,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN);
       constexpr uint32_t SBO_A = C::HALO_W * 128;
       const uint32_t smA_u32 = ptx::smem_u32(smA);
       const uint32_t smB_u32 = ptx::smem_u32(smB);
@@ -253,7 +261,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
                   const uint32_t bo_a = args.desc_base_mode ? ((aa >> 7) & 7) : 0;
                   const uint64_t adesc = ptx::make_desc_k_sw128(aa, SBO_A, bo_a);
                   const uint64_t bdesc = ptx::make_desc_k_sw128(bb, 1024, 0);
-                  ptx::umma_bf16(acc0 + j * BN, adesc, bdesc, idesc, (k == 0) ? first : 1u);
+                  ptx::umma_f16(acc0 + j * BN, adesc, bdesc, idesc, (k == 0) ? first : 1u);
                 }
               }
               ptx::umma_commit(&bEmpty[bst]);
@@ -340,8 +348,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
             const int co = n0 - tap * args.cout1;
             if (valid_hw) {
               const int od = 2 * d + (tap >> 2), oh = 2 * h + ((tap >> 1) & 1), ow = 2 * w + (tap & 1);
-              __nv_bfloat16* dst =
-                  args.out_bf16 +
+              __half* dst =
+                  args.out_f16 +
                   (((static_cast<size_t>(t.nb) * (2 * args.D) + od) * (2 * args.H) + oh) * (2 * args.W) + ow) *
                       args.ld1 +
                   args.coff1 + co;
@@ -354,8 +362,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
                 for (int e = 0; e < 4; ++e) {
                   const float lo = __uint_as_float(raw[8 * i + 2 * e]) + __ldg(bp + 8 * i + 2 * e);
                   const float hi = __uint_as_float(raw[8 * i + 2 * e + 1]) + __ldg(bp + 8 * i + 2 * e + 1);
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
-                  pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                  pk[e] = pack_half2_sat(lo, hi);
                 }
                 dst4[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
@@ -400,7 +407,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
 // Packed image: [n_tile][chunk][tap][row r < BN][128 B], 16-byte unit j of row r stored at unit j ^ (r & 7).
 // conv:  w is OIDHW fp32 (Cout, Cin, k, k, k); GEMM column n = output channel.
 // convT: w is IODHW fp32 (Cin, Cout, 2, 2, 2); GEMM column n = tap * Cout + co with tap = (a*2+b)*2+c.
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+__global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
                                     int taps, int BN, int transposed) {
   const int chunks = Cin / 64;
   const int ngemm = transposed ? 8 * Cout : Cout;
@@ -427,7 +434,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     }
     const size_t stage = (static_cast<size_t>(n_tile) * chunks + chunk) * gtaps + tap;
     const size_t off = stage * BN * 64 + static_cast<size_t>(r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
-    out[off] = __float2bfloat16_rn(v);
+    out[off] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
   }
 }
 
@@ -440,7 +447,7 @@ static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, 
                            (cuuint64_t)D * H * W * C * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)boxW, (cuuint32_t)boxH, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -504,7 +511,7 @@ int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const 
   a.W = W, a.H = H, a.D = D, a.NB = NB;
   a.chunks = Cin / 64;
   a.wpacked = static_cast<const uint8_t*>(wpacked);
-  a.out_bf16 = static_cast<__nv_bfloat16*>(y);
+  a.out_f16 = static_cast<__half*>(y);
   a.bias = bias;
   a.ld1 = y_ld, a.coff1 = y_coff, a.cout1 = Cout;
   a.n_tiles = 8 * Cout / 128;
@@ -520,7 +527,7 @@ int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int tra
   const int BN = transposed ? 128 : conv3d_k3_bn(Cout);
   const int ngemm = transposed ? 8 * Cout : Cout;
   if (ngemm % BN) return set_error("pack_weights: GEMM N not a multiple of the N tile");
-  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), Cout, Cin, taps, BN,
+  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<__half*>(out), Cout, Cin, taps, BN,
                                                          transposed);
   NC_CUDA(cudaGetLastError());
   return 0;

@@ -2,7 +2,7 @@
 // finalize/apply(+pool), the 1x1x1+sigmoid head, overlap blend, radix-select percentile, rescale/cast/crop and
 // the max-intensity projection.  All are coalesced, vectorised where the layout allows, and bit-exact where the
 // reference is integer / fixed-order fp32 arithmetic.  Reference citations are in include/neuroclear_b200.h.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "internal.h"
 
@@ -199,8 +199,9 @@ int in_stats_finalize(const float* partial, int NB, long long rows, int C, long 
   return 0;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  // InstanceNorm outputs are bounded by sqrt(#voxels) << 65504, the clamp only guards degenerate inputs
+  __half2 t = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -216,7 +217,7 @@ __device__ __forceinline__ void norm8(const float* __restrict__ src, const float
 
 __global__ void __launch_bounds__(256)
 in_relu_apply_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, long long voxels, int C,
-                     __nv_bfloat16* __restrict__ y, int y_ld, int y_coff) {
+                     __half* __restrict__ y, int y_ld, int y_coff) {
   const int nb = blockIdx.y;
   const int cg_per = C / 8;
   const long long total = voxels * cg_per;
@@ -232,16 +233,16 @@ in_relu_apply_kernel(const float* __restrict__ raw, const float* __restrict__ me
     }
     const long long gv = static_cast<long long>(nb) * voxels + vox;
     norm8(raw + gv * C + cg * 8, mu, rs, o);
-    uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                          pack_bf16x2(o[6], o[7]));
+    uint4 pk = make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]),
+                          pack_f16x2(o[6], o[7]));
     *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pk;
   }
 }
 
 __global__ void __launch_bounds__(256)
 in_relu_pool_apply_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
-                          int C, __nv_bfloat16* __restrict__ y, int y_ld, int y_coff,
-                          __nv_bfloat16* __restrict__ pooled) {
+                          int C, __half* __restrict__ y, int y_ld, int y_coff,
+                          __half* __restrict__ pooled) {
   const int nb = blockIdx.y;
   const int cg_per = C / 8;
   const int PD = D / 2, PH = H / 2, PW = W / 2;
@@ -269,15 +270,15 @@ in_relu_pool_apply_kernel(const float* __restrict__ raw, const float* __restrict
       const long long gv = ((static_cast<long long>(nb) * D + dz) * H + hy) * W + wx;
       float o[8];
       norm8(raw + gv * C + cg * 8, mu, rs, o);
-      uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                            pack_bf16x2(o[6], o[7]));
+      uint4 pk = make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]),
+                            pack_f16x2(o[6], o[7]));
       *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pk;
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], o[i]);
     }
     const long long pv = ((static_cast<long long>(nb) * PD + pd) * PH + ph) * PW + pw;
-    uint4 pk = make_uint4(pack_bf16x2(mx[0], mx[1]), pack_bf16x2(mx[2], mx[3]), pack_bf16x2(mx[4], mx[5]),
-                          pack_bf16x2(mx[6], mx[7]));
+    uint4 pk = make_uint4(pack_f16x2(mx[0], mx[1]), pack_f16x2(mx[2], mx[3]), pack_f16x2(mx[4], mx[5]),
+                          pack_f16x2(mx[6], mx[7]));
     *reinterpret_cast<uint4*>(pooled + pv * C + cg * 8) = pk;
   }
 }
@@ -290,11 +291,11 @@ int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H
   if (pooled) {
     if ((D | H | W) & 1) return set_error("in_relu_apply: pooling needs even D, H, W");
     in_relu_pool_apply_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, D, H, W, C,
-                                                                    static_cast<__nv_bfloat16*>(y), y_ld, y_coff,
-                                                                    static_cast<__nv_bfloat16*>(pooled));
+                                                                    static_cast<__half*>(y), y_ld, y_coff,
+                                                                    static_cast<__half*>(pooled));
   } else {
     in_relu_apply_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, static_cast<long long>(D) * H * W, C,
-                                                               static_cast<__nv_bfloat16*>(y), y_ld, y_coff);
+                                                               static_cast<__half*>(y), y_ld, y_coff);
   }
   NC_CUDA(cudaGetLastError());
   return 0;

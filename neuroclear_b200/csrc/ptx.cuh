@@ -102,8 +102,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32, single-CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]; fp16 x fp16 -> fp32 (kind::f16), single-CTA.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -137,7 +137,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, bf16:
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, 16-bit elements:
 //   rows are 128 B apart inside an 8-row group, groups are `sbo_bytes` apart (any multiple of 16).
 //   The XOR swizzle acts on absolute shared-memory address bits, so any 128 B-aligned start is a valid
 //   window into a TMA-written (SWIZZLE_128B) row array.
@@ -151,9 +151,10 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr, uint32
   d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: bf16 A/B (K-major both), fp32 accumulate, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// Instruction descriptor: fp16 A/B (format 0; bf16 would be 1 at bits 7 and 10), both K-major, fp32 accumulate
+// (c_format 1 at bit 4), M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -112,7 +112,7 @@ class Unet_deconv(nn.Module):
         self._engine = None
         self._engine_sig = None
 
-    # the packed bf16 weight cache follows the parameters: any in-place update, load_state_dict or device move
+    # the packed fp16 weight cache follows the parameters: any in-place update, load_state_dict or device move
     # changes (data_ptr, _version) and triggers a repack on the next forward.
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())

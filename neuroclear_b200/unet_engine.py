@@ -4,15 +4,15 @@ Data layout in HBM (per batch of NB cubes of D x H x W voxels, L0 = full, L1 = /
 
     x      fp32 (NB, L0)            dice output / network input
     raw0   fp32 (NB, L0, 64)        raw conv output of U1, U2, U12 (reused, consumed before rewritten)
-    a1     bf16 (NB, L0, 64)        IN+ReLU(U1)
-    cat1   bf16 (NB, L0, 128)       [IN+ReLU(U2) | t_conv1]          = torch.cat([conv1, t_conv1], 1)
-    p1     bf16 (NB, L1, 64)        maxpool1
+    a1     fp16 (NB, L0, 64)        IN+ReLU(U1)
+    cat1   fp16 (NB, L0, 128)       [IN+ReLU(U2) | t_conv1]          = torch.cat([conv1, t_conv1], 1)
+    p1     fp16 (NB, L1, 64)        maxpool1
     raw1   fp32 (NB, L1, 128)       raw output of U3, U4, U9, U10
-    a3     bf16 (NB, L1, 128)       IN+ReLU(U3) / (U9) / (U10)
-    cat2   bf16 (NB, L1, 256)       [IN+ReLU(U4) | t_conv2]          = torch.cat([conv2, t_conv2], 1)
-    p2     bf16 (NB, L2, 128)       maxpool2
+    a3     fp16 (NB, L1, 128)       IN+ReLU(U3) / (U9) / (U10)
+    cat2   fp16 (NB, L1, 256)       [IN+ReLU(U4) | t_conv2]          = torch.cat([conv2, t_conv2], 1)
+    p2     fp16 (NB, L2, 128)       maxpool2
     raw2   fp32 (NB, L2, 256)       raw output of U5, U6, U7
-    b1,b2  bf16 (NB, L2, 256)       bottom-layer ping-pong
+    b1,b2  fp16 (NB, L2, 256)       bottom-layer ping-pong
     y      fp32 (NB, L0 - 2*crop)   sigmoid output, border already cut
 
 All activations are NDHWC; the concat buffers make torch.cat a no-op (producers write channel slices).
@@ -91,7 +91,7 @@ class UnetDeconvEngine:
         self._ws = None  # release before allocating the new one
         dev = self.device
         l0, l1, l2 = d * h * w, (d // 2) * (h // 2) * (w // 2), (d // 4) * (h // 4) * (w // 4)
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = torch.float16, torch.float32
         e = lambda n, dt: torch.empty(n, dtype=dt, device=dev)
         lib = _lib.load()
         rows = max(

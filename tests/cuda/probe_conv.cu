@@ -3,7 +3,7 @@
 // result must equal a plain CPU direct convolution BIT FOR BIT.  Usage:
 //   probe_conv check <case> <desc_base_mode>     -> prints PASS/FAIL
 //   probe_conv time  <case> <nb> <iters>         -> prints TFLOP/s of one layer shape
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <chrono>
@@ -55,10 +55,10 @@ static const int ncases = sizeof(cases) / sizeof(cases[0]);
 static int run_check(const Case& c, int mode) {
   const size_t vox = (size_t)c.NB * c.D * c.H * c.W;
   std::vector<float> x(vox * c.Cin);
-  std::vector<__nv_bfloat16> xb(x.size());
+  std::vector<__half> xb(x.size());
   for (size_t i = 0; i < x.size(); ++i) {
     x[i] = ((int)(rnd() % 9) - 4) / 4.0f;
-    xb[i] = __float2bfloat16(x[i]);
+    xb[i] = __float2half(x[i]);
   }
   const int taps = c.transposed ? 8 : 27;
   std::vector<float> w((size_t)c.Cout * c.Cin * taps);
@@ -150,7 +150,7 @@ static int run_check(const Case& c, int mode) {
     CK(cudaMemset(dy, 0, ovox * ld * 2));
     NCK(nc_convT3d_k2s2_fwd(dx, c.NB, c.D, c.H, c.W, c.Cin, dp, dbias, c.Cout, dy, ld, coff, nullptr));
     CK(cudaDeviceSynchronize());
-    std::vector<__nv_bfloat16> y(ovox * ld);
+    std::vector<__half> y(ovox * ld);
     CK(cudaMemcpy(y.data(), dy, y.size() * 2, cudaMemcpyDeviceToHost));
 #pragma omp parallel for collapse(2) reduction(+ : bad) reduction(max : maxerr)
     for (int n = 0; n < c.NB; ++n)
@@ -164,12 +164,12 @@ static int run_check(const Case& c, int mode) {
               float acc = 0.f;
               for (int ci = 0; ci < c.Cin; ++ci) acc += xp[ci] * w[((size_t)ci * c.Cout + co) * 8 + tap];
               acc += bias[co];
-              const float ref = __bfloat162float(__float2bfloat16(acc));
-              const float g = __bfloat162float(y[ov * ld + coff + co]);
+              const float ref = __half2float(__float2half(acc));
+              const float g = __half2float(y[ov * ld + coff + co]);
               const double e = fabs((double)g - (double)ref);
               if (!(e == 0.0)) ++bad;
               if (e > maxerr || e != e) maxerr = (e != e) ? 1e30 : e;
-              if (__bfloat162float(y[ov * ld + co]) != 0.f) ++bad;  // lower half must stay untouched
+              if (__half2float(y[ov * ld + co]) != 0.f) ++bad;  // lower half must stay untouched
             }
           }
     printf("%s: %lld mismatching outputs, max |err| %.4g -> %s\n", c.name, bad, maxerr, bad == 0 ? "PASS" : "FAIL");

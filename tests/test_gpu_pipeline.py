@@ -30,7 +30,13 @@ def _oracle_pipeline(vol, sd, roi, ov, bc, normalize):
     return outs, blend, final, pcts
 
 
-def _volume(shape, seed=0):
+def _volume(shape, seed=0, roi=24, ov=6, bc=4):
+    """Fluorescence-like volume.  Value parity needs every cube to contain some data: a cube lying entirely in
+    pad_for_dicing's zero padding is degenerate in the reference itself (InstanceNorm of constant channels
+    amplifies fp32 rounding noise by 1/sqrt(eps) per layer — see DESIGN.md), so shapes with such cubes are only
+    used for the finite-output test below."""
+    step = roi - ov
+    assert all(((n + ov) // step) * step - bc < n for n in shape), "shape has pure-padding cubes"
     rng = np.random.default_rng(seed)
     return (rng.random(shape) ** 3 * 65535).astype(np.uint16)
 
@@ -40,7 +46,7 @@ def test_drop_in_loop_like_test_dice(cuda):
     from neuroclear_b200 import networks
     from neuroclear_b200.dicing import Assemble_Dice, DiceImageDataSet
     roi, ov, bc = 24, 6, 4                                   # cube edge 32
-    vol = _volume((40, 52, 30))
+    vol = _volume((40, 58, 38))
     sd = ounet.random_state_dict(seed=0, bias_std=0.1)
     opt = _opt(roi, ov, bc)
     dataset = DiceImageDataSet(opt, volume=vol)
@@ -83,7 +89,7 @@ def test_drop_in_loop_like_test_dice(cuda):
 def test_fused_pipeline_matches_oracle(cuda, normalize):
     from neuroclear_b200.pipeline import DicedInference
     roi, ov, bc = 24, 6, 4
-    vol = _volume((33, 47, 61), seed=2)
+    vol = _volume((40, 47, 61), seed=2)
     sd = ounet.random_state_dict(seed=0, bias_std=0.1)
     pipe = DicedInference(sd, cuda, roi, ov, bc, normalize_intensity=normalize, batch=5)
     got, (z0, z1) = pipe.run(vol)
@@ -100,7 +106,7 @@ def test_fused_pipeline_matches_oracle(cuda, normalize):
 def test_config1_128_cube_geometry_and_one_cube(cuda):
     """BASELINE config 1: 128^3 volume, dice 120 / overlap 15 / border 10 -> 8 cubes of 140^3."""
     from neuroclear_b200.pipeline import DicedInference
-    vol = _volume((128, 128, 128), seed=4)
+    vol = _volume((128, 128, 128), seed=4, roi=120, ov=15, bc=10)
     sd = ounet.random_state_dict(seed=0, bias_std=0.1)
     pipe = DicedInference(sd, cuda, 120, 15, 10, normalize_intensity=True, batch=4)
     plan = pipe.plan(vol.shape)
@@ -135,3 +141,19 @@ def test_identity_network_roundtrip_large(cuda):
     assert np.abs(out.astype(np.int64) - vol.astype(np.int64)).max() <= 1
     # the padded region of the blend is exactly zero, the overlap count never exceeds 8
     assert float(vis[vol.shape[0]:].abs().max()) == 0.0
+
+
+def test_pure_padding_cubes_stay_finite(cuda):
+    """(n + overlap) % step < overlap puts whole cubes into the zero padding (here z: 30 -> cubes at 0, 18, 36).
+    Their reference output is amplified rounding noise (no parity possible); ours must simply be finite and the
+    data region must still match the oracle where only data-bearing cubes contribute."""
+    from neuroclear_b200.pipeline import DicedInference
+    roi, ov, bc = 24, 6, 4
+    rng = np.random.default_rng(6)
+    vol = (rng.random((30, 40, 40)) ** 3 * 65535).astype(np.uint16)
+    sd = ounet.random_state_dict(seed=0, bias_std=0.1)
+    pipe = DicedInference(sd, cuda, roi, ov, bc, normalize_intensity=False, batch=3)
+    got, _ = pipe.run(vol)
+    assert got.shape == vol.shape
+    outs, blend, final, _ = _oracle_pipeline(vol, sd, roi, ov, bc, False)
+    assert np.abs(got.astype(np.int64) - final.astype(np.int64)).max() <= 2e-2 * 65535 + 2

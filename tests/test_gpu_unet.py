@@ -87,9 +87,10 @@ def test_weight_updates_invalidate_packed_cache(net, cuda):
     m = net.module
     with torch.no_grad():
         y0 = net(x)
+        saved = m.one_by_one_2.bias.clone()
         m.one_by_one_2.bias.add_(1.0)                 # what an optimiser step does (in-place, bumps _version)
         y1 = net(x)
-        m.one_by_one_2.bias.sub_(1.0)
+        m.one_by_one_2.bias.copy_(saved)
         y2 = net(x)
     assert not torch.equal(y0, y1) and torch.equal(y0, y2)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}                      # save_networks round trip
