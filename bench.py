@@ -270,7 +270,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "fp16", "data": "synthetic", "config": cfg,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": ms_e / args.steps, "clocks": clocks_e},

@@ -82,10 +82,13 @@ int nc_convT3d_k2s2_fwd(const void* x_f16, int32_t nb, int32_t d, int32_t h, int
                         const void* packed, const float* bias, int32_t cout, void* y_f16, int32_t y_ld,
                         int32_t y_coff, nc_stream_t stream);
 
-/* InstanceNorm3d(affine=False, eps) statistics (networks.py:33-34): deterministic fixed-order reduction of the
- * per-tile partials in fp64 -> mean_rstd float32 (NB, 2, C): [:,0,:] = mean, [:,1,:] = 1/sqrt(var_biased+eps). */
+/* InstanceNorm3d(affine=False, eps) statistics (networks.py:33-34): deterministic fixed-order two-level reduction
+ * of the per-tile partials in fp64 -> mean_rstd float32 (NB, 2, C): [:,0,:] = mean, [:,1,:] = 1/sqrt(var_biased+eps).
+ * scratch: device buffer of nc_in_stats_scratch_bytes(nb, c) bytes, ZERO-FILLED once by the caller before its first
+ * use (it holds arrival counters the kernel resets itself) and reusable across calls on one stream. */
+int64_t nc_in_stats_scratch_bytes(int32_t nb, int32_t c);
 int nc_in_stats_finalize(const float* stats_partial, int32_t nb, int64_t rows_per_sample, int32_t c,
-                         int64_t voxels_per_sample, float eps, float* mean_rstd, nc_stream_t stream);
+                         int64_t voxels_per_sample, float eps, void* scratch, float* mean_rstd, nc_stream_t stream);
 
 /* InstanceNorm apply + ReLU (+ MaxPool3d(2), networks.py:491,494) + write into a concat slice:
  * y[..., y_coff:y_coff+C] = fp16(relu((raw - mean) * rstd)); if pooled != NULL also the 2x2x2 max as fp16

@@ -64,24 +64,17 @@ int nc_pack_weights_convT3d_k2s2(const float* w, int32_t cin, int32_t cout, void
 
 int nc_conv3d_k3_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
                      int32_t cout, float* y_raw, float* stats_partial, nc_stream_t stream) {
-  return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, 0, S(stream));
+  return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, S(stream));
 }
-// Not part of the public header: lets the hardware probe choose how the shared-memory descriptor's base-offset
-// field is filled for tap-shifted windows (0 = zero, 1 = (addr >> 7) & 7).
-int nc_probe_conv3d_k3_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
-                           const void* packed, int32_t cout, float* y_raw, float* stats_partial, int32_t mode,
-                           nc_stream_t stream) {
-  return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, mode, S(stream));
-}
-
 int nc_convT3d_k2s2_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
                         const float* bias, int32_t cout, void* y, int32_t y_ld, int32_t y_coff, nc_stream_t stream) {
   return convT3d_k2s2_fwd(x, nb, d, h, w, cin, packed, bias, cout, y, y_ld, y_coff, S(stream));
 }
 
+int64_t nc_in_stats_scratch_bytes(int32_t nb, int32_t c) { return static_cast<int64_t>(in_stats_scratch_bytes(nb, c)); }
 int nc_in_stats_finalize(const float* partial, int32_t nb, int64_t rows, int32_t c, int64_t voxels, float eps,
-                         float* mean_rstd, nc_stream_t stream) {
-  return in_stats_finalize(partial, nb, rows, c, voxels, eps, mean_rstd, S(stream));
+                         void* scratch, float* mean_rstd, nc_stream_t stream) {
+  return in_stats_finalize(partial, nb, rows, c, voxels, eps, scratch, mean_rstd, S(stream));
 }
 
 int nc_in_relu_apply(const float* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t c,

@@ -70,7 +70,6 @@ struct ConvTcArgs {
   __half* out_f16;  // [NB][2D][2H][2W][ld1]
   const float* bias;
   int ld1, coff1, cout1;
-  int desc_base_mode;  // 0: base_offset field = 0 (absolute-address swizzle); 1: (addr>>7)&7
 };
 
 struct TileCoord {
@@ -213,86 +212,92 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN);
-      constexpr uint32_t SBO_A = C::HALO_W * 128;
-      const uint32_t smA_u32 = ptx::smem_u32(smA);
-      const uint32_t smB_u32 = ptx::smem_u32(smB);
-      int pslot = 0;  // ring position of plane 0 of the current (tile, chunk)
-      uint32_t pph = 0;
-      int bst = 0;
-      uint32_t bph = 0;
-      int it = 0;
-      for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = static_cast<uint32_t>(it >> 1);
-        ptx::mbar_wait(&accEmpty[buf], (use & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * C::ACC_COLS;
-        for (int c = 0; c < args.chunks; ++c) {
-          int waited = 0;
-          for (int kd = 0; kd < KS; ++kd) {
-            for (; waited <= TD - 1 + kd; ++waited) {
-              int s = pslot + waited;
-              uint32_t p = pph;
-              if (s >= C::NSLOT) {
-                s -= C::NSLOT;
-                p ^= 1;
-              }
-              ptx::mbar_wait(&planeFull[s], p);
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp walks the (warp-uniform) loops so that every address / descriptor lives in uniform
+    // registers; one elected lane issues the tcgen05 instructions.  (Issuing from a divergent single-lane
+    // region makes the compiler broadcast each operand through R2UR per MMA, which costs more than the MMA.)
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN);
+    // high descriptor words are constant: SBO [32,46), version 1 at bit 46, SWIZZLE_128B (2) at [61,64)
+    constexpr uint32_t A_HI = ((C::HALO_W * 128u) >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t LO_FLAGS = 1u << 16;  // LBO field = 1 (ignored for swizzled K-major)
+    const uint32_t smA_u32 = ptx::smem_u32(smA);
+    const uint32_t smB_u32 = ptx::smem_u32(smB);
+    int pslot = 0;  // ring position of plane 0 of the current (tile, chunk)
+    uint32_t pph = 0;
+    int bst = 0;
+    uint32_t bph = 0;
+    int it = 0;
+    for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      ptx::mbar_wait(&accEmpty[buf], (use & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * C::ACC_COLS;
+      for (int c = 0; c < args.chunks; ++c) {
+        int waited = 0;
+        for (int kd = 0; kd < KS; ++kd) {
+          for (; waited <= TD - 1 + kd; ++waited) {
+            int s = pslot + waited;
+            uint32_t p = pph;
+            if (s >= C::NSLOT) {
+              s -= C::NSLOT;
+              p ^= 1;
             }
+            ptx::mbar_wait(&planeFull[s], p);
+          }
+          ptx::tc_fence_after();
+          for (int khw = 0; khw < KS * KS; ++khw) {
+            const int kh = khw / KS, kw = khw - kh * KS;
+            ptx::mbar_wait(&bFull[bst], bph);
             ptx::tc_fence_after();
-            for (int khw = 0; khw < KS * KS; ++khw) {
-              const int kh = khw / KS, kw = khw - kh * KS;
-              ptx::mbar_wait(&bFull[bst], bph);
-              ptx::tc_fence_after();
-              const uint32_t b_addr = smB_u32 + bst * C::BSTAGE_BYTES;
-              const uint32_t first = (c == 0 && kd == 0 && khw == 0) ? 0u : 1u;
+            const uint32_t b_lo = (((smB_u32 + bst * C::BSTAGE_BYTES) >> 4) & 0x3FFF) | LO_FLAGS;
+            const uint32_t first = (c == 0 && kd == 0 && khw == 0) ? 0u : 1u;
+            const uint32_t tap_off = (kh * C::HALO_W + kw) * 128;
+            if (ptx::elect_one()) {
 #pragma unroll
               for (int j = 0; j < TD; ++j) {
                 int s = pslot + j + kd;
                 if (s >= C::NSLOT) s -= C::NSLOT;
-                const uint32_t a_addr = smA_u32 + s * C::PLANE_BYTES + (kh * C::HALO_W + kw) * 128;
+                const uint32_t a_lo = (((smA_u32 + s * C::PLANE_BYTES + tap_off) >> 4) & 0x3FFF) | LO_FLAGS;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint32_t aa = a_addr + k * 32;
-                  const uint32_t bb = b_addr + k * 32;
-                  const uint32_t bo_a = args.desc_base_mode ? ((aa >> 7) & 7) : 0;
-                  const uint64_t adesc = ptx::make_desc_k_sw128(aa, SBO_A, bo_a);
-                  const uint64_t bdesc = ptx::make_desc_k_sw128(bb, 1024, 0);
+                  const uint64_t adesc = (static_cast<uint64_t>(A_HI) << 32) | (a_lo + 2 * k);
+                  const uint64_t bdesc = (static_cast<uint64_t>(B_HI) << 32) | (b_lo + 2 * k);
                   ptx::umma_f16(acc0 + j * BN, adesc, bdesc, idesc, (k == 0) ? first : 1u);
                 }
               }
               ptx::umma_commit(&bEmpty[bst]);
-              if (++bst == C::NBST) {
-                bst = 0;
-                bph ^= 1;
+              // planes whose last reader was this kd group go back to the producer
+              if (khw == KS * KS - 1) {
+                if (kd < KS - 1) {
+                  int s = pslot + kd;
+                  if (s >= C::NSLOT) s -= C::NSLOT;
+                  ptx::umma_commit(&planeEmpty[s]);
+                } else {
+                  for (int i = KS - 1; i < C::PPC; ++i) {
+                    int s = pslot + i;
+                    if (s >= C::NSLOT) s -= C::NSLOT;
+                    ptx::umma_commit(&planeEmpty[s]);
+                  }
+                  if (c == args.chunks - 1) ptx::umma_commit(&accFull[buf]);
+                }
               }
             }
-            // planes whose last reader was this kd group go back to the producer
-            if (kd < KS - 1) {
-              int s = pslot + kd;
-              if (s >= C::NSLOT) s -= C::NSLOT;
-              ptx::umma_commit(&planeEmpty[s]);
-            } else {
-              for (int i = KS - 1; i < C::PPC; ++i) {
-                int s = pslot + i;
-                if (s >= C::NSLOT) s -= C::NSLOT;
-                ptx::umma_commit(&planeEmpty[s]);
-              }
+            __syncwarp();
+            if (++bst == C::NBST) {
+              bst = 0;
+              bph ^= 1;
             }
-          }
-          pslot += C::PPC;
-          if (pslot >= C::NSLOT) {
-            pslot -= C::NSLOT;
-            pph ^= 1;
           }
         }
-        ptx::umma_commit(&accFull[buf]);
+        pslot += C::PPC;
+        if (pslot >= C::NSLOT) {
+          pslot -= C::NSLOT;
+          pph ^= 1;
+        }
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;    // TMEM lane quarter this warp may access
@@ -484,7 +489,7 @@ size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout) {
 }
 
 int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, float* y_raw,
-                  float* stats_partial, int desc_base_mode, cudaStream_t stream) {
+                  float* stats_partial, cudaStream_t stream) {
   if (Cin % 64 || Cout % 64) return set_error("conv3d_k3_fwd: Cin and Cout must be multiples of 64");
   ConvTcArgs a{};
   a.W = W, a.H = H, a.D = D, a.NB = NB;
@@ -493,7 +498,6 @@ int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const voi
   a.out_raw = y_raw;
   a.stats_partial = stats_partial;
   a.ldo = Cout;
-  a.desc_base_mode = desc_base_mode;
   if (Cout == 64) {
     a.n_tiles = 1;
     return launch_cfg<3, 64, 3, 0>(x, a, Cin, stream);

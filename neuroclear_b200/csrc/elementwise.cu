@@ -159,42 +159,82 @@ int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
-__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int C, double inv_n,
-                                         float eps, float* __restrict__ mean_rstd) {
+// Two-level fixed-order reduction in fp64: grid (C/32, NB, S). Every block sums one slice of the partial rows
+// (8 row-lanes x 32 channels, combined in a fixed order), stores its slice total, and the LAST block to finish for
+// a (sample, channel group) — found with an arrival counter — adds the S slice totals in slice order and writes
+// mean / rstd.  The summation order never depends on scheduling, so results are bitwise repeatable.
+constexpr int FIN_SLICES = 64;
+
+__global__ void __launch_bounds__(256)
+in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int C, double inv_n, float eps,
+                         double* __restrict__ slice_tot, unsigned int* __restrict__ counters,
+                         float* __restrict__ mean_rstd) {
   __shared__ double ssum[8][32], ssq[8][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  const int nb = blockIdx.y;
+  __shared__ bool is_last;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int nb = blockIdx.y, slice = blockIdx.z, S = gridDim.z;
+  const long long per = (rows + S - 1) / S;
+  const long long r0 = slice * per, r1 = min(rows, r0 + per);
   double s = 0.0, q = 0.0;
   if (c < C) {
     const float* p = partial + static_cast<size_t>(nb) * rows * 2 * C;
-    for (long long r = threadIdx.y; r < rows; r += 8) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
       s += static_cast<double>(p[(r * 2) * C + c]);
       q += static_cast<double>(p[(r * 2 + 1) * C + c]);
     }
   }
-  ssum[threadIdx.y][threadIdx.x] = s;
-  ssq[threadIdx.y][threadIdx.x] = q;
+  ssum[ty][tx] = s;
+  ssq[ty][tx] = q;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    double S = 0.0, Q = 0.0;
+  double* tot = slice_tot + ((static_cast<size_t>(nb) * S + slice) * 2) * C;
+  if (ty == 0 && c < C) {
+    double S1 = 0.0, Q1 = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      S += ssum[i][threadIdx.x];
-      Q += ssq[i][threadIdx.x];
+      S1 += ssum[i][tx];
+      Q1 += ssq[i][tx];
     }
-    const double mean = S * inv_n;
-    double var = Q * inv_n - mean * mean;
+    tot[c] = S1;
+    tot[C + c] = Q1;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* cnt = counters + nb * gridDim.x + blockIdx.x;
+    const unsigned int prev = atomicAdd(cnt, 1u);
+    is_last = (prev == static_cast<unsigned int>(S - 1));
+    if (is_last) *cnt = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (is_last && ty == 0 && c < C) {
+    __threadfence();
+    double S1 = 0.0, Q1 = 0.0;
+    const double* base = slice_tot + (static_cast<size_t>(nb) * S * 2) * C;
+    for (int i = 0; i < S; ++i) {
+      S1 += __ldcg(base + (static_cast<size_t>(i) * 2) * C + c);
+      Q1 += __ldcg(base + (static_cast<size_t>(i) * 2 + 1) * C + c);
+    }
+    const double mean = S1 * inv_n;
+    double var = Q1 * inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     mean_rstd[(static_cast<size_t>(nb) * 2) * C + c] = static_cast<float>(mean);
     mean_rstd[(static_cast<size_t>(nb) * 2 + 1) * C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
 }
 
-int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps,
+size_t in_stats_scratch_bytes(int NB, int C) {
+  return static_cast<size_t>(NB) * FIN_SLICES * 2 * C * sizeof(double) + static_cast<size_t>(NB) * ((C + 31) / 32) * 4 + 256;
+}
+
+int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps, void* scratch,
                       float* mean_rstd, cudaStream_t stream) {
-  dim3 grid((C + 31) / 32, NB), block(32, 8);
-  in_stats_finalize_kernel<<<grid, block, 0, stream>>>(partial, rows, C, 1.0 / static_cast<double>(voxels), eps,
-                                                       mean_rstd);
+  if (NB > 65535) return set_error("in_stats_finalize: NB too large");
+  double* slice_tot = static_cast<double*>(scratch);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(slice_tot + static_cast<size_t>(NB) * FIN_SLICES * 2 * C);
+  dim3 grid((C + 31) / 32, NB, FIN_SLICES);
+  in_stats_finalize_kernel<<<grid, 256, 0, stream>>>(partial, rows, C, 1.0 / static_cast<double>(voxels), eps,
+                                                     slice_tot, counters, mean_rstd);
   NC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,7 +31,7 @@ int conv3d_k3_bn(int Cout);
 int conv3d_k3_td(int Cout);
 size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout);
 int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, float* y_raw,
-                  float* stats_partial, int desc_base_mode, cudaStream_t stream);
+                  float* stats_partial, cudaStream_t stream);
 int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, const float* bias,
                      int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream);
 size_t packed_weight_bytes(int Cout, int Cin, int taps, int transposed);
@@ -45,7 +45,8 @@ int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, con
 size_t conv_cin1_stats_tiles(int NB, int D, int H, int W);
 int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, float* y_raw,
                        float* stats_partial, cudaStream_t stream);
-int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps,
+size_t in_stats_scratch_bytes(int NB, int C);
+int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps, void* scratch,
                       float* mean_rstd, cudaStream_t stream);
 int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
                   int y_coff, void* pooled, cudaStream_t stream);

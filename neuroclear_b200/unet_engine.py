@@ -105,6 +105,7 @@ class UnetDeconvEngine:
             raw1=e(nb * l1 * 128, f32), a3=e(nb * l1 * 128, bf), cat2=e(nb * l1 * 256, bf), p2=e(nb * l2 * 128, bf),
             raw2=e(nb * l2 * 256, f32), b1=e(nb * l2 * 256, bf), b2=e(nb * l2 * 256, bf),
             stats=e(rows * 2, f32), mr=e(nb * 2 * 256, f32),
+            fin=torch.zeros(lib.nc_in_stats_scratch_bytes(nb, 256), dtype=torch.uint8, device=dev),
         )
         self._ws_key, self._ws = key, ws
         return ws
@@ -133,7 +134,8 @@ class UnetDeconvEngine:
 
         def stats(cin, dd, hh, ww, c):
             rows = lib.nc_conv3d_k3_stats_rows(cin, nb, dd, hh, ww, c)
-            call("nc_in_stats_finalize", ptr(st), nb, i64(rows // nb), c, i64(dd * hh * ww), IN_EPS, ptr(mr), s)
+            call("nc_in_stats_finalize", ptr(st), nb, i64(rows // nb), c, i64(dd * hh * ww), IN_EPS, ptr(ws["fin"]),
+                 ptr(mr), s)
 
         def conv(prefix, src, dd, hh, ww, cin, cout, raw):
             if self.profile is not None:

@@ -1,7 +1,7 @@
 // Standalone hardware probe for the tcgen05 convolution kernels, driven through the public C ABI.
 // Exact-arithmetic inputs (small dyadic rationals) make the fp32 accumulation order-independent, so the GPU
 // result must equal a plain CPU direct convolution BIT FOR BIT.  Usage:
-//   probe_conv check <case> <desc_base_mode>     -> prints PASS/FAIL
+//   probe_conv check <case>                      -> prints PASS/FAIL
 //   probe_conv time  <case> <nb> <iters>         -> prints TFLOP/s of one layer shape
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -15,8 +15,6 @@
 
 #include "../../include/neuroclear_b200.h"
 
-extern "C" int nc_probe_conv3d_k3_fwd(const void*, int32_t, int32_t, int32_t, int32_t, int32_t, const void*, int32_t,
-                                      float*, float*, int32_t, nc_stream_t);
 
 #define CK(x)                                                                        \
   do {                                                                               \
@@ -85,7 +83,7 @@ static int run_check(const Case& c, int mode) {
     CK(cudaMalloc(&dy, vox * c.Cout * 4));
     CK(cudaMemset(dy, 0xFF, vox * c.Cout * 4));
     CK(cudaMalloc(&dst, rows * 2 * c.Cout * 4));
-    NCK(nc_probe_conv3d_k3_fwd(dx, c.NB, c.D, c.H, c.W, c.Cin, dp, c.Cout, dy, dst, mode, nullptr));
+    NCK(nc_conv3d_k3_fwd(dx, c.NB, c.D, c.H, c.W, c.Cin, dp, c.Cout, dy, dst, nullptr));
     CK(cudaDeviceSynchronize());
     std::vector<float> y(vox * c.Cout), st(rows * 2 * c.Cout);
     CK(cudaMemcpy(y.data(), dy, y.size() * 4, cudaMemcpyDeviceToHost));

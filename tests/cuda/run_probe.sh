@@ -7,13 +7,8 @@ LOG=gpurun_out/probe.log
 : > $LOG
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $LOG 2>&1
 P=build/probe_conv
-for mode in 0 1; do
-  for c in 0 1 2 3 4; do
-    timeout 120 $P check $c $mode >> $LOG 2>&1 || echo "case $c mode $mode exit=$?" >> $LOG
-  done
-done
-for c in 5 6; do
-  timeout 120 $P check $c 0 >> $LOG 2>&1 || echo "case $c exit=$?" >> $LOG
+for c in 0 1 2 3 4 5 6; do
+  timeout 120 $P check $c >> $LOG 2>&1 || echo "case $c exit=$?" >> $LOG
 done
 if [ "$1" != "notime" ]; then
   for s in 0 1 2 3 4 5 6 7 8; do

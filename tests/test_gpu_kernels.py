@@ -121,7 +121,10 @@ def _finalize(lib, st, cin, nb, d, h, w, c, cuda):
     from neuroclear_b200._lib import call, i64, ptr, stream_ptr
     rows = lib.nc_conv3d_k3_stats_rows(cin, nb, d, h, w, c)
     mr = torch.empty(nb * 2 * c, dtype=torch.float32, device=cuda)
-    call("nc_in_stats_finalize", ptr(st), nb, i64(rows // nb), c, i64(d * h * w), 1e-5, ptr(mr), stream_ptr())
+    scratch = torch.zeros(lib.nc_in_stats_scratch_bytes(nb, c), dtype=torch.uint8, device=cuda)
+    for _ in range(2):          # the arrival counters reset themselves: a second launch must give the same answer
+        call("nc_in_stats_finalize", ptr(st), nb, i64(rows // nb), c, i64(d * h * w), 1e-5, ptr(scratch), ptr(mr),
+             stream_ptr())
     return mr.view(nb, 2, c)
 
 
