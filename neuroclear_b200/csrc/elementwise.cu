@@ -223,15 +223,21 @@ in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int 
   }
 }
 
+// scratch layout: [arrival counters: FIN_COUNTER_BYTES, at a FIXED offset so that calls with different (NB, C)
+// sharing one scratch buffer never overwrite each other's counters][slice totals: NB x S x 2 x C doubles]
+constexpr size_t FIN_COUNTER_BYTES = 65536;
+
 size_t in_stats_scratch_bytes(int NB, int C) {
-  return static_cast<size_t>(NB) * FIN_SLICES * 2 * C * sizeof(double) + static_cast<size_t>(NB) * ((C + 31) / 32) * 4 + 256;
+  return FIN_COUNTER_BYTES + static_cast<size_t>(NB) * FIN_SLICES * 2 * C * sizeof(double);
 }
 
 int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps, void* scratch,
                       float* mean_rstd, cudaStream_t stream) {
   if (NB > 65535) return set_error("in_stats_finalize: NB too large");
-  double* slice_tot = static_cast<double*>(scratch);
-  unsigned int* counters = reinterpret_cast<unsigned int*>(slice_tot + static_cast<size_t>(NB) * FIN_SLICES * 2 * C);
+  if (static_cast<size_t>(NB) * ((C + 31) / 32) * 4 > FIN_COUNTER_BYTES)
+    return set_error("in_stats_finalize: NB * C too large for the counter region");
+  unsigned int* counters = static_cast<unsigned int*>(scratch);
+  double* slice_tot = reinterpret_cast<double*>(static_cast<char*>(scratch) + FIN_COUNTER_BYTES);
   dim3 grid((C + 31) / 32, NB, FIN_SLICES);
   in_stats_finalize_kernel<<<grid, 256, 0, stream>>>(partial, rows, C, 1.0 / static_cast<double>(voxels), eps,
                                                      slice_tot, counters, mean_rstd);

@@ -254,3 +254,22 @@ def test_mip_forward_backward(cuda, lib):
     pc, _ = omip.get_projection(vc, 5, 1)
     pc.backward(gout.cpu())
     assert torch.equal(v.grad.cpu(), vc.grad)
+
+
+def test_stats_finalize_shared_scratch_across_channel_counts(cuda, lib):
+    """One scratch buffer serves calls with different (NB, C), as UnetDeconvEngine does layer after layer."""
+    from neuroclear_b200._lib import call, i64, ptr, stream_ptr
+    g = torch.Generator().manual_seed(3)
+    scratch = torch.zeros(lib.nc_in_stats_scratch_bytes(3, 256), dtype=torch.uint8, device=cuda)
+    for rep in range(2):
+        for nb, c, rows in [(3, 64, 500), (2, 256, 77), (1, 128, 1000), (3, 64, 9)]:
+            part = torch.rand((nb, rows, 2, c), generator=g) + 0.5
+            pd = part.to(cuda)
+            mr = torch.empty((nb, 2, c), device=cuda)
+            n = rows * 384
+            call("nc_in_stats_finalize", ptr(pd), nb, i64(rows), c, i64(n), 1e-5, ptr(scratch), ptr(mr), stream_ptr())
+            s1, s2 = part[:, :, 0].double().sum(1), part[:, :, 1].double().sum(1)
+            mean = s1 / n
+            var = (s2 / n - mean * mean).clamp_min(0)
+            got = mr.cpu().double()
+            assert torch.allclose(got[:, 0], mean, rtol=1e-6) and torch.allclose(got[:, 1], 1 / torch.sqrt(var + 1e-5), rtol=1e-5)
