@@ -116,7 +116,7 @@ def cpu_baseline_sample(shape, threads=None):
     return voxels / total, cores, sample, t_cube + t_asm * gs.n_cubes / g.n_cubes
 
 
-def run_reference(args, shape):
+def run_reference(args, shape, guard):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -130,7 +130,7 @@ def run_reference(args, shape):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.prod(shape)) / value * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "f32", "data": "synthetic",
         "config": workload_config(shape, None, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -139,7 +139,7 @@ def run_reference(args, shape):
                 "the Python reference itself cannot travel to the GPU box; each step is a bounded sample, ms_per_step "
                 "is the extrapolated whole-volume time",
     }
-    print(json.dumps(line))
+    guard.emit(json.dumps(line))
 
 
 def workload_config(shape, batch, gpus):
@@ -150,7 +150,22 @@ def workload_config(shape, batch, gpus):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+class StdoutGuard:
+    """Libraries (NCCL's version banner, torch warnings) may print to fd 1; the driver wants exactly ONE JSON line
+    there.  Everything written to fd 1 while the guard is active goes to stderr; emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -163,7 +178,7 @@ def main():
     shape = tuple(args.size)
 
     if args.impl == "reference":
-        return run_reference(args, shape)
+        return run_reference(args, shape, guard)
 
     import torch.distributed as dist
     from neuroclear_b200 import _lib
@@ -280,7 +295,7 @@ def main():
             "tensor_pipe_frac_whole_step": FLOP_PER_VOXEL * geo.n_cubes * geo.edge ** 3 * args.steps
                                             / (ms * 1e-3) / 1e12 / peak / world,
         }
-        print(json.dumps(line))
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
