@@ -11,7 +11,7 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, one host thread per
  *     device; return value 0 = OK, negative = error with the message in nc_last_error() (thread-local).
  *   - activations between the tensor-core convolutions are fp16, NDHWC ("channels-last-3d"); convolution
- *     outputs that feed InstanceNorm are raw fp32 NDHWC plus per-tile statistics partials.
+ *     outputs that feed InstanceNorm are raw fp16 NDHWC plus per-tile fp32 statistics partials.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with an error.
  */
 #ifndef NEUROCLEAR_B200_H_
@@ -33,6 +33,9 @@ int nc_abi_version(void);
 const char* nc_last_error(void);
 /* number of SMs of the current device (148 on B200); <0 on error */
 int nc_device_sm_count(void);
+/* test hook: cap the persistent grid of the tensor-core conv kernels at n CTAs (0 = one per SM) so that small test
+ * problems also exercise the several-tiles-per-CTA path (ring wrap-around, accumulator ping-pong) */
+void nc_debug_set_max_ctas(int32_t n);
 
 /* ---- dicing geometry (host-only integer math) --------------------------------------------------------------
  * util/util.py:196-215 pad_for_dicing  +  data/diceImage_dataset.py:82-106 DiceCube.__init__/indexToCoordinates
@@ -58,9 +61,10 @@ int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, i
 
 /* double_conv1.convolution.0 (networks.py:420,490): Conv3d(1 -> Cout, k3 s1 p1), fp32 CUDA-core direct conv.
  * x: float32 (NB,D,H,W); w: float32 (Cout,1,3,3,3) as stored in the state_dict; Cout must be 64.
- * y_raw: float32 NDHWC (NB,D,H,W,Cout) WITHOUT bias (a bias in front of InstanceNorm(affine=False) cancels). */
+ * y_raw: fp16 NDHWC (NB,D,H,W,Cout) WITHOUT bias (a bias in front of InstanceNorm(affine=False) cancels); the
+ * statistics partials are taken from the fp32 values before the fp16 store. */
 int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d, int32_t h, int32_t wdt, int32_t cout,
-                          float* y_raw, float* stats_partial, nc_stream_t stream);
+                          void* y_raw, float* stats_partial, nc_stream_t stream);
 
 /* Packed weight sizes / packing for the tensor-core kernels.  conv: w is OIDHW float32 (Cout,Cin,3,3,3);
  * convT: w is IODHW float32 (Cin,Cout,2,2,2) (torch ConvTranspose3d layout).  Output is the fp16 swizzled
@@ -71,9 +75,10 @@ int nc_pack_weights_convT3d_k2s2(const float* w_iodhw, int32_t cin, int32_t cout
 
 /* nn.Conv3d(Cin -> Cout, k3 s1 p1) of double_conv / triple_conv / last_conv (networks.py:413-476): tcgen05
  * implicit GEMM, fp16 operands, fp32 accumulate.  x: fp16 NDHWC (NB,D,H,W,Cin) (Cin may be a concat buffer);
- * y_raw: float32 NDHWC (NB,D,H,W,Cout) without bias; stats_partial as above.  Cin % 64 == 0, Cout in {64,128k}. */
+ * y_raw: fp16 NDHWC (NB,D,H,W,Cout) without bias; stats_partial (from the fp32 accumulators) as above.
+ * Cin % 64 == 0, Cout in {64,128k}. */
 int nc_conv3d_k3_fwd(const void* x_f16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
-                     int32_t cout, float* y_raw, float* stats_partial, nc_stream_t stream);
+                     int32_t cout, void* y_raw, float* stats_partial, nc_stream_t stream);
 
 /* nn.ConvTranspose3d(Cin -> Cout, k2 s2) t_conv2 / t_conv1 (networks.py:500,503) fused with the channel concat
  * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as fp16 into
@@ -92,15 +97,15 @@ int nc_in_stats_finalize(const float* stats_partial, int32_t nb, int64_t rows_pe
 
 /* InstanceNorm apply + ReLU (+ MaxPool3d(2), networks.py:491,494) + write into a concat slice:
  * y[..., y_coff:y_coff+C] = fp16(relu((raw - mean) * rstd)); if pooled != NULL also the 2x2x2 max as fp16
- * NDHWC (NB,D/2,H/2,W/2,C).  raw: float32 NDHWC. */
-int nc_in_relu_apply(const float* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+ * NDHWC (NB,D/2,H/2,W/2,C).  raw: fp16 NDHWC (normalised in fp32). */
+int nc_in_relu_apply(const void* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
                      int32_t c, void* y_f16, int32_t y_ld, int32_t y_coff, void* pooled_f16, nc_stream_t stream);
 
 /* Tail of Unet_deconv.forward (networks.py:504-510,533-536): InstanceNorm+ReLU of ex_conv1_1, one_by_one (C->1),
  * one_by_one_2 (1->1) and sigmoid in one pass; optionally drops `crop` voxels per side (the border cut of
  * util/assemble_dice.py:143).  head_params (device float32): [w1[0..C), b1, w2, b2].
- * raw: float32 NDHWC (NB,D,H,W,C); y: float32 (NB, D-2crop, H-2crop, W-2crop). */
-int nc_head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* head_params, int32_t nb,
+ * raw: fp16 NDHWC (NB,D,H,W,C); y: float32 (NB, D-2crop, H-2crop, W-2crop). */
+int nc_head_1x1_sigmoid_fwd(const void* raw, const float* mean_rstd, const float* head_params, int32_t nb,
                             int32_t d, int32_t h, int32_t w, int32_t c, int32_t crop, float* y, nc_stream_t stream);
 
 /* ---- assembly (util/assemble_dice.py:161-213) ---------------------------------------------------------------

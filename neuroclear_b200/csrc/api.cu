@@ -12,6 +12,8 @@ extern "C" {
 int nc_abi_version(void) { return NC_ABI_VERSION; }
 const char* nc_last_error(void) { return last_error(); }
 
+void nc_debug_set_max_ctas(int32_t n) { debug_set_max_ctas(n); }
+
 int nc_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("no CUDA device");
@@ -48,7 +50,7 @@ int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, i
 }
 
 int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d, int32_t h, int32_t wdt, int32_t cout,
-                          float* y_raw, float* stats_partial, nc_stream_t stream) {
+                          void* y_raw, float* stats_partial, nc_stream_t stream) {
   return conv3d_cin1_k3_fwd(x, w, nb, d, h, wdt, cout, y_raw, stats_partial, S(stream));
 }
 
@@ -63,7 +65,7 @@ int nc_pack_weights_convT3d_k2s2(const float* w, int32_t cin, int32_t cout, void
 }
 
 int nc_conv3d_k3_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
-                     int32_t cout, float* y_raw, float* stats_partial, nc_stream_t stream) {
+                     int32_t cout, void* y_raw, float* stats_partial, nc_stream_t stream) {
   return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, S(stream));
 }
 int nc_convT3d_k2s2_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
@@ -77,12 +79,12 @@ int nc_in_stats_finalize(const float* partial, int32_t nb, int64_t rows, int32_t
   return in_stats_finalize(partial, nb, rows, c, voxels, eps, scratch, mean_rstd, S(stream));
 }
 
-int nc_in_relu_apply(const float* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t c,
+int nc_in_relu_apply(const void* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t c,
                      void* y, int32_t y_ld, int32_t y_coff, void* pooled, nc_stream_t stream) {
   return in_relu_apply(raw, mean_rstd, nb, d, h, w, c, y, y_ld, y_coff, pooled, S(stream));
 }
 
-int nc_head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* hp, int32_t nb, int32_t d,
+int nc_head_1x1_sigmoid_fwd(const void* raw, const float* mean_rstd, const float* hp, int32_t nb, int32_t d,
                             int32_t h, int32_t w, int32_t c, int32_t crop, float* y, nc_stream_t stream) {
   return head_1x1_sigmoid_fwd(raw, mean_rstd, hp, nb, d, h, w, c, crop, y, S(stream));
 }

@@ -15,7 +15,7 @@
 //   * warp roles: 0 = halo-plane TMA producer, 1 = MMA issuer, 2 = TMEM allocator + weight producer,
 //     4..7 = epilogue (TMEM -> registers -> global). Two accumulator sets ping-pong so the epilogue of
 //     tile i overlaps the MMAs of tile i+1. The grid is persistent (<= #SMs CTAs, static tile stride).
-//   * epilogue MODE 0: raw fp32 NDHWC store + per-tile per-channel (sum, sum of squares) partials taken from
+//   * epilogue MODE 0: raw fp16 NDHWC store + per-tile per-channel (sum, sum of squares) partials taken from
 //     the fp32 accumulators (InstanceNorm statistics, reduced deterministically later);
 //     MODE 1: transposed-conv scatter (voxel (2d+a,2h+b,2w+c)), +bias, fp16 store into a channel slice of the
 //     skip-concat buffer.
@@ -31,7 +31,12 @@ constexpr int TH = 16;  // tile extent in h  (number of 8-row groups of a 128-ro
 
 constexpr int pow2_at_least(int v) { return v <= 32 ? 32 : v <= 64 ? 64 : v <= 128 ? 128 : v <= 256 ? 256 : 512; }
 
-template <int KS, int BN, int TD>
+// STACK (Cout = 64 only): the three kd taps of one (kh,kw) are stacked along the MMA N dimension — one read of a
+// shifted A window feeds the accumulators of up to three output planes (N = 64/128/192) instead of one, which takes
+// the kernel off the shared-memory-bandwidth roof an N = 64 MMA sits on (4 KB of A per 32 math cycles).  A tile is
+// TD = 4 output planes processed in two phases of three input planes; each phase walks all nine (kh,kw) weight
+// stages (192 rows = [kd2 | kd1 | kd0]), so the 6-slot plane ring always prefetches the next phase's planes.
+template <int KS, int BN, int TD, bool STACK = false>
 struct ConvCfg {
   static constexpr int PAD = KS / 2;
   static constexpr int HALO_W = TW + KS - 1;
@@ -40,9 +45,10 @@ struct ConvCfg {
   static constexpr int PLANE_BOX_BYTES = PLANE_ROWS * 128;
   static constexpr int PLANE_BYTES = (PLANE_BOX_BYTES + 1023) / 1024 * 1024;
   static constexpr int PPC = TD + KS - 1;  // halo planes per (tile, chunk)
-  static constexpr int NSLOT = PPC + 2;    // plane ring depth: two planes of look-ahead
+  static constexpr int NSLOT = STACK ? PPC : PPC + 2;  // plane ring depth (two planes / one phase of look-ahead)
   static constexpr int TAPS = KS * KS * KS;
-  static constexpr int BSTAGE_BYTES = BN * 128;
+  static constexpr int BSTAGE_BYTES = (STACK ? 3 * BN : BN) * 128;
+  static constexpr int STAGES_PER_CHUNK = STACK ? 2 * KS * KS : KS * KS * KS;
   static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4;  // barriers + per-warp stats scratch
   static constexpr int SMEM_LIMIT = 232448;
   static constexpr int NBST_FIT = (SMEM_LIMIT - 1024 - AUX_BYTES - NSLOT * PLANE_BYTES) / BSTAGE_BYTES;
@@ -53,17 +59,19 @@ struct ConvCfg {
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(NBST >= 2, "weight ring too shallow");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "bad BN");
+  static_assert(!STACK || (KS == 3 && BN == 64 && TD == 4), "STACK is built for k3, Cout 64, four output planes");
 };
 
 struct ConvTcArgs {
   int W, H, D, NB;
+  int max_ctas;  // persistent grid size cap (debug hook: forces several tiles per CTA on small problems)
   int chunks;  // Cin / 64
   int n_tiles;  // GEMM N / BN
   int tiles_w, tiles_h, tiles_d;
   int total_tiles;
   const uint8_t* wpacked;
   // MODE 0
-  float* out_raw;        // [NB][D][H][W][ldo]
+  __half* out_raw;       // [NB][D][H][W][ldo] raw conv output, fp16
   float* stats_partial;  // [spatial tile][2][ldo]
   int ldo;               // total output channels (row pitch of out_raw)
   // MODE 1
@@ -117,10 +125,10 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int KS, int BN, int TD, int MODE>
+template <int KS, int BN, int TD, int MODE, bool STACK>
 __global__ void __launch_bounds__(256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs args) {
-  using C = ConvCfg<KS, BN, TD>;
+  using C = ConvCfg<KS, BN, TD, STACK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -195,13 +203,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
       uint32_t ph = 0;
       for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
         const TileCoord t = decode_tile(args, tile, TD);
+        // packed stages per chunk: 27 taps, or (STACK) 9 (kh,kw) blocks of 192 rows walked once per phase
+        constexpr int PACKED_PER_CHUNK = STACK ? KS * KS : C::TAPS;
         const uint8_t* wsrc =
-            args.wpacked + static_cast<size_t>(t.n_tile) * args.chunks * C::TAPS * C::BSTAGE_BYTES;
-        const int nst = args.chunks * C::TAPS;
+            args.wpacked + static_cast<size_t>(t.n_tile) * args.chunks * PACKED_PER_CHUNK * C::BSTAGE_BYTES;
+        const int nst = args.chunks * C::STAGES_PER_CHUNK;
         for (int s = 0; s < nst; ++s) {
+          const int cc = s / C::STAGES_PER_CHUNK;
+          const int src = cc * PACKED_PER_CHUNK + (s - cc * C::STAGES_PER_CHUNK) % PACKED_PER_CHUNK;
           ptx::mbar_wait(&bEmpty[st], ph ^ 1);
           ptx::mbar_arrive_expect_tx(&bFull[st], C::BSTAGE_BYTES);
-          ptx::bulk_load(smB + st * C::BSTAGE_BYTES, wsrc + static_cast<size_t>(s) * C::BSTAGE_BYTES,
+          ptx::bulk_load(smB + st * C::BSTAGE_BYTES, wsrc + static_cast<size_t>(src) * C::BSTAGE_BYTES,
                          C::BSTAGE_BYTES, &bFull[st]);
           if (++st == C::NBST) {
             st = 0;
@@ -235,59 +247,130 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
       ptx::tc_fence_after();
       const uint32_t acc0 = tmem_base + buf * C::ACC_COLS;
       for (int c = 0; c < args.chunks; ++c) {
-        int waited = 0;
-        for (int kd = 0; kd < KS; ++kd) {
-          for (; waited <= TD - 1 + kd; ++waited) {
-            int s = pslot + waited;
-            uint32_t p = pph;
-            if (s >= C::NSLOT) {
-              s -= C::NSLOT;
-              p ^= 1;
-            }
-            ptx::mbar_wait(&planeFull[s], p);
-          }
-          ptx::tc_fence_after();
-          for (int khw = 0; khw < KS * KS; ++khw) {
-            const int kh = khw / KS, kw = khw - kh * KS;
-            ptx::mbar_wait(&bFull[bst], bph);
-            ptx::tc_fence_after();
-            const uint32_t b_lo = (((smB_u32 + bst * C::BSTAGE_BYTES) >> 4) & 0x3FFF) | LO_FLAGS;
-            const uint32_t first = (c == 0 && kd == 0 && khw == 0) ? 0u : 1u;
-            const uint32_t tap_off = (kh * C::HALO_W + kw) * 128;
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int j = 0; j < TD; ++j) {
-                int s = pslot + j + kd;
-                if (s >= C::NSLOT) s -= C::NSLOT;
-                const uint32_t a_lo = (((smA_u32 + s * C::PLANE_BYTES + tap_off) >> 4) & 0x3FFF) | LO_FLAGS;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t adesc = (static_cast<uint64_t>(A_HI) << 32) | (a_lo + 2 * k);
-                  const uint64_t bdesc = (static_cast<uint64_t>(B_HI) << 32) | (b_lo + 2 * k);
-                  ptx::umma_f16(acc0 + j * BN, adesc, bdesc, idesc, (k == 0) ? first : 1u);
-                }
+        if constexpr (STACK) {
+          constexpr uint32_t idesc64 = ptx::make_idesc_f16(128, 64), idesc128 = ptx::make_idesc_f16(128, 128),
+                             idesc192 = ptx::make_idesc_f16(128, 192);
+          for (int phase = 0; phase < 2; ++phase) {
+            for (int i = 0; i < 3; ++i) {
+              int s = pslot + 3 * phase + i;
+              uint32_t p = pph;
+              if (s >= C::NSLOT) {
+                s -= C::NSLOT;
+                p ^= 1;
               }
-              ptx::umma_commit(&bEmpty[bst]);
-              // planes whose last reader was this kd group go back to the producer
-              if (khw == KS * KS - 1) {
-                if (kd < KS - 1) {
-                  int s = pslot + kd;
+              ptx::mbar_wait(&planeFull[s], p);
+            }
+            ptx::tc_fence_after();
+            for (int khw = 0; khw < 9; ++khw) {
+              const int kh = khw / 3, kw = khw - kh * 3;
+              ptx::mbar_wait(&bFull[bst], bph);
+              ptx::tc_fence_after();
+              const uint32_t b_lo = (((smB_u32 + bst * C::BSTAGE_BYTES) >> 4) & 0x3FFF) | LO_FLAGS;
+              const uint32_t tap_off = (kh * C::HALO_W + kw) * 128;
+              const bool first_tap = (c == 0 && khw == 0);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                  const int pi = 3 * phase + i;                    // input plane 0..5 of this (tile, chunk)
+                  const int j_lo = pi - 2 > 0 ? pi - 2 : 0;        // output planes fed by this input plane
+                  const int j_hi = pi < 3 ? pi : 3;
+                  int s = pslot + pi;
                   if (s >= C::NSLOT) s -= C::NSLOT;
-                  ptx::umma_commit(&planeEmpty[s]);
-                } else {
-                  for (int i = KS - 1; i < C::PPC; ++i) {
-                    int s = pslot + i;
+                  const uint32_t a_lo = (((smA_u32 + s * C::PLANE_BYTES + tap_off) >> 4) & 0x3FFF) | LO_FLAGS;
+                  if (first_tap) {
+                    // the first MMA into an accumulator must overwrite it: issue this tap unstacked, kd = 0 first
+                    for (int j = j_hi; j >= j_lo; --j) {
+                      const int kd = pi - j;
+                      const uint32_t bj = b_lo + (((2 - kd) * 64 * 128) >> 4);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(acc0 + j * 64, (static_cast<uint64_t>(A_HI) << 32) | (a_lo + 2 * k),
+                                      (static_cast<uint64_t>(B_HI) << 32) | (bj + 2 * k), idesc64,
+                                      (kd == 0 && k == 0) ? 0u : 1u);
+                    }
+                  } else {
+                    // rows [ (2-kd_max)*64, ... ) of the [kd2|kd1|kd0] stage line up with columns j_lo..j_hi
+                    const int nj = j_hi - j_lo + 1;
+                    const uint32_t bj = b_lo + (((2 - (pi - j_lo)) * 64 * 128) >> 4);
+                    const uint32_t idn = nj == 1 ? idesc64 : nj == 2 ? idesc128 : idesc192;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      ptx::umma_f16(acc0 + j_lo * 64, (static_cast<uint64_t>(A_HI) << 32) | (a_lo + 2 * k),
+                                    (static_cast<uint64_t>(B_HI) << 32) | (bj + 2 * k), idn, 1u);
+                  }
+                }
+                ptx::umma_commit(&bEmpty[bst]);
+                if (khw == 8) {
+                  for (int i = 0; i < 3; ++i) {
+                    int s = pslot + 3 * phase + i;
                     if (s >= C::NSLOT) s -= C::NSLOT;
                     ptx::umma_commit(&planeEmpty[s]);
                   }
-                  if (c == args.chunks - 1) ptx::umma_commit(&accFull[buf]);
+                  if (phase == 1 && c == args.chunks - 1) ptx::umma_commit(&accFull[buf]);
                 }
               }
+              __syncwarp();
+              if (++bst == C::NBST) {
+                bst = 0;
+                bph ^= 1;
+              }
             }
-            __syncwarp();
-            if (++bst == C::NBST) {
-              bst = 0;
-              bph ^= 1;
+          }
+        } else {
+          int waited = 0;
+          for (int kd = 0; kd < KS; ++kd) {
+            for (; waited <= TD - 1 + kd; ++waited) {
+              int s = pslot + waited;
+              uint32_t p = pph;
+              if (s >= C::NSLOT) {
+                s -= C::NSLOT;
+                p ^= 1;
+              }
+              ptx::mbar_wait(&planeFull[s], p);
+            }
+            ptx::tc_fence_after();
+            for (int khw = 0; khw < KS * KS; ++khw) {
+              const int kh = khw / KS, kw = khw - kh * KS;
+              ptx::mbar_wait(&bFull[bst], bph);
+              ptx::tc_fence_after();
+              const uint32_t b_lo = (((smB_u32 + bst * C::BSTAGE_BYTES) >> 4) & 0x3FFF) | LO_FLAGS;
+              const uint32_t first = (c == 0 && kd == 0 && khw == 0) ? 0u : 1u;
+              const uint32_t tap_off = (kh * C::HALO_W + kw) * 128;
+              if (ptx::elect_one()) {
+  #pragma unroll
+                for (int j = 0; j < TD; ++j) {
+                  int s = pslot + j + kd;
+                  if (s >= C::NSLOT) s -= C::NSLOT;
+                  const uint32_t a_lo = (((smA_u32 + s * C::PLANE_BYTES + tap_off) >> 4) & 0x3FFF) | LO_FLAGS;
+  #pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t adesc = (static_cast<uint64_t>(A_HI) << 32) | (a_lo + 2 * k);
+                    const uint64_t bdesc = (static_cast<uint64_t>(B_HI) << 32) | (b_lo + 2 * k);
+                    ptx::umma_f16(acc0 + j * BN, adesc, bdesc, idesc, (k == 0) ? first : 1u);
+                  }
+                }
+                ptx::umma_commit(&bEmpty[bst]);
+                // planes whose last reader was this kd group go back to the producer
+                if (khw == KS * KS - 1) {
+                  if (kd < KS - 1) {
+                    int s = pslot + kd;
+                    if (s >= C::NSLOT) s -= C::NSLOT;
+                    ptx::umma_commit(&planeEmpty[s]);
+                  } else {
+                    for (int i = KS - 1; i < C::PPC; ++i) {
+                      int s = pslot + i;
+                      if (s >= C::NSLOT) s -= C::NSLOT;
+                      ptx::umma_commit(&planeEmpty[s]);
+                    }
+                    if (c == args.chunks - 1) ptx::umma_commit(&accFull[buf]);
+                  }
+                }
+              }
+              __syncwarp();
+              if (++bst == C::NBST) {
+                bst = 0;
+                bph ^= 1;
+              }
             }
           }
         }
@@ -330,13 +413,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
           if constexpr (MODE == 0) {
             const int co = t.n_tile * BN + cc * 32;
             if (valid_hw) {
-              float4* dst = reinterpret_cast<float4*>(
+              uint4* dst = reinterpret_cast<uint4*>(
                   args.out_raw + (((static_cast<size_t>(t.nb) * args.D + d) * args.H + h) * args.W + w) * args.ldo +
                   co);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
-                                     __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+              for (int i = 0; i < 4; ++i)
+                dst[i] = make_uint4(pack_half2_sat(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
+                                    pack_half2_sat(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
+                                    pack_half2_sat(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
+                                    pack_half2_sat(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
             }
             float v[32], v2[32];
 #pragma unroll
@@ -412,8 +497,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
 // Packed image: [n_tile][chunk][tap][row r < BN][128 B], 16-byte unit j of row r stored at unit j ^ (r & 7).
 // conv:  w is OIDHW fp32 (Cout, Cin, k, k, k); GEMM column n = output channel.
 // convT: w is IODHW fp32 (Cin, Cout, 2, 2, 2); GEMM column n = tap * Cout + co with tap = (a*2+b)*2+c.
+// stacked (conv, Cout = 64): [chunk][kh*3+kw][row = (2-kd)*64 + co][128 B], i.e. stages of 192 rows [kd2|kd1|kd0].
 __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
-                                    int taps, int BN, int transposed) {
+                                    int taps, int BN, int transposed, int stacked) {
   const int chunks = Cin / 64;
   const int ngemm = transposed ? 8 * Cout : Cout;
   const int gtaps = transposed ? 1 : taps;
@@ -437,8 +523,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
       const int t8 = n / Cout, co = n - t8 * Cout;
       v = w[(static_cast<size_t>(ci) * Cout + co) * 8 + t8];
     }
-    const size_t stage = (static_cast<size_t>(n_tile) * chunks + chunk) * gtaps + tap;
-    const size_t off = stage * BN * 64 + static_cast<size_t>(r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
+    size_t off;
+    if (stacked) {
+      const int kd = tap / 9, khw = tap - kd * 9;
+      const int row = (2 - kd) * 64 + r;
+      off = (static_cast<size_t>(chunk) * 9 + khw) * 192 * 64 + static_cast<size_t>(row) * 64 +
+            ((((k >> 3) ^ (row & 7)) << 3) | (k & 7));
+    } else {
+      const size_t stage = (static_cast<size_t>(n_tile) * chunks + chunk) * gtaps + tap;
+      off = stage * BN * 64 + static_cast<size_t>(r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
+    }
     out[off] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
   }
 }
@@ -459,48 +553,52 @@ static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, 
   return 0;
 }
 
-template <int KS, int BN, int TD, int MODE>
+static int g_max_ctas = 0;  // 0 = one CTA per SM
+void debug_set_max_ctas(int n) { g_max_ctas = n; }
+
+template <int KS, int BN, int TD, int MODE, bool STACK = false>
 static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
-  using C = ConvCfg<KS, BN, TD>;
+  using C = ConvCfg<KS, BN, TD, STACK>;
   CUtensorMap tm;
   if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H)) return rc;
   a.tiles_w = (a.W + TW - 1) / TW;
   a.tiles_h = (a.H + TH - 1) / TH;
   a.tiles_d = (a.D + TD - 1) / TD;
   a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
-  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE>;
+  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK>;
   static bool attr_set = false;
   if (!attr_set) {
     NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
+  const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
+  const int grid = a.total_tiles < cap ? a.total_tiles : cap;
   kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, a);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
 
 int conv3d_k3_bn(int Cout) { return Cout == 64 ? 64 : 128; }
-int conv3d_k3_td(int Cout) { return Cout == 64 ? 3 : 2; }
+int conv3d_k3_td(int Cout) { return Cout == 64 ? 4 : 2; }
 
 size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout) {
   const int td = conv3d_k3_td(Cout);
   return static_cast<size_t>(NB) * ((D + td - 1) / td) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
 }
 
-int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, float* y_raw,
+int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, void* y_raw,
                   float* stats_partial, cudaStream_t stream) {
   if (Cin % 64 || Cout % 64) return set_error("conv3d_k3_fwd: Cin and Cout must be multiples of 64");
   ConvTcArgs a{};
   a.W = W, a.H = H, a.D = D, a.NB = NB;
   a.chunks = Cin / 64;
   a.wpacked = static_cast<const uint8_t*>(wpacked);
-  a.out_raw = y_raw;
+  a.out_raw = static_cast<__half*>(y_raw);
   a.stats_partial = stats_partial;
   a.ldo = Cout;
   if (Cout == 64) {
     a.n_tiles = 1;
-    return launch_cfg<3, 64, 3, 0>(x, a, Cin, stream);
+    return launch_cfg<3, 64, 4, 0, true>(x, a, Cin, stream);
   }
   if (Cout % 128) return set_error("conv3d_k3_fwd: Cout must be 64 or a multiple of 128");
   a.n_tiles = Cout / 128;
@@ -532,7 +630,7 @@ int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int tra
   const int ngemm = transposed ? 8 * Cout : Cout;
   if (ngemm % BN) return set_error("pack_weights: GEMM N not a multiple of the N tile");
   pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<__half*>(out), Cout, Cin, taps, BN,
-                                                         transposed);
+                                                         transposed, (!transposed && Cout == 64) ? 1 : 0);
   NC_CUDA(cudaGetLastError());
   return 0;
 }

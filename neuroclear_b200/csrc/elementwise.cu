@@ -62,24 +62,29 @@ int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, con
 }
 
 // ------------------------------------------------------------------------------------------------ first layer
-constexpr int C1_TW = 28, C1_TH = 8, C1_WSTEP = 4;
+// Conv3d(1 -> 64, k3 p1) in fp32 on the CUDA cores.  Block = 8 warps on a 28(w) x 16(h) x 1(d) tile staged with its
+// halo in shared memory; a warp owns two h-rows, a lane two output channels (its 54 weights live in registers) and
+// walks the row in steps of 4 voxels: per (kd,kh) it broadcast-loads 6 inputs with one LDS.128 + one LDS.64 and
+// issues 24 FMAs.  Stores are fp16 pairs (128 B per voxel per warp), statistics come from the fp32 values.
+constexpr int C1_TW = 28, C1_TH = 16, C1_WSTEP = 4, C1_PITCH = 32;
 
 __global__ void __launch_bounds__(256)
 conv_cin1_k3_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int D, int H, int W, int tiles_w,
-                    int tiles_h, float* __restrict__ y_raw, float* __restrict__ stats_partial) {
-  __shared__ float halo[3][C1_TH + 2][C1_TW + 4];
+                    int tiles_h, __half* __restrict__ y_raw, float* __restrict__ stats_partial) {
+  __shared__ __align__(16) float halo[3][C1_TH + 2][C1_PITCH];
   __shared__ float red[8][2][64];
   const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
   const int d = blockIdx.y, nb = blockIdx.z;
   const int w0 = tw * C1_TW, h0 = th * C1_TH;
   const float* xin = x + static_cast<size_t>(nb) * D * H * W;
-  for (int i = threadIdx.x; i < 3 * (C1_TH + 2) * (C1_TW + 2); i += 256) {
-    const int ww = i % (C1_TW + 2);
-    const int hh = (i / (C1_TW + 2)) % (C1_TH + 2);
-    const int dd = i / ((C1_TW + 2) * (C1_TH + 2));
+  for (int i = threadIdx.x; i < 3 * (C1_TH + 2) * C1_PITCH; i += 256) {
+    const int ww = i % C1_PITCH;
+    const int hh = (i / C1_PITCH) % (C1_TH + 2);
+    const int dd = i / (C1_PITCH * (C1_TH + 2));
     const int gz = d - 1 + dd, gy = h0 - 1 + hh, gx = w0 - 1 + ww;
     float v = 0.f;
-    if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) v = xin[(static_cast<size_t>(gz) * H + gy) * W + gx];
+    if (ww < C1_TW + 2 && gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = xin[(static_cast<size_t>(gz) * H + gy) * W + gx];
     halo[dd][hh][ww] = v;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,9 +95,12 @@ conv_cin1_k3_kernel(const float* __restrict__ x, const float* __restrict__ wgt, 
     w1r[t] = __ldg(wgt + (2 * lane + 1) * 27 + t);
   }
   __syncthreads();
-  const int h = h0 + warp;
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  if (h < H) {
+#pragma unroll 1
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = warp + 8 * rr;
+    const int h = h0 + row;
+    if (h >= H) break;
 #pragma unroll 1
     for (int s = 0; s < C1_TW / C1_WSTEP; ++s) {
       float acc0[C1_WSTEP], acc1[C1_WSTEP];
@@ -102,9 +110,9 @@ conv_cin1_k3_kernel(const float* __restrict__ x, const float* __restrict__ wgt, 
       for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          float in[C1_WSTEP + 2];
-#pragma unroll
-          for (int i = 0; i < C1_WSTEP + 2; ++i) in[i] = halo[kd][warp + kh][s * C1_WSTEP + i];
+          const float4 a = *reinterpret_cast<const float4*>(&halo[kd][row + kh][s * C1_WSTEP]);
+          const float2 b = *reinterpret_cast<const float2*>(&halo[kd][row + kh][s * C1_WSTEP + 4]);
+          const float in[C1_WSTEP + 2] = {a.x, a.y, a.z, a.w, b.x, b.y};
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
@@ -117,9 +125,9 @@ conv_cin1_k3_kernel(const float* __restrict__ x, const float* __restrict__ wgt, 
       for (int v = 0; v < C1_WSTEP; ++v) {
         const int w = w0 + s * C1_WSTEP + v;
         if (w < W) {
-          float2* dst = reinterpret_cast<float2*>(
+          __half2* dst = reinterpret_cast<__half2*>(
               y_raw + ((((static_cast<size_t>(nb) * D + d) * H + h) * W + w) * 64 + 2 * lane));
-          *dst = make_float2(acc0[v], acc1[v]);
+          *dst = __floats2half2_rn(fminf(fmaxf(acc0[v], -65504.f), 65504.f), fminf(fmaxf(acc1[v], -65504.f), 65504.f));
           s0 += acc0[v];
           s1 += acc1[v];
           q0 = fmaf(acc0[v], acc0[v], q0);
@@ -147,13 +155,14 @@ size_t conv_cin1_stats_tiles(int NB, int D, int H, int W) {
   return static_cast<size_t>(NB) * D * ((H + C1_TH - 1) / C1_TH) * ((W + C1_TW - 1) / C1_TW);
 }
 
-int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, float* y_raw,
+int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, void* y_raw,
                        float* stats_partial, cudaStream_t stream) {
   if (Cout != 64) return set_error("conv3d_cin1_k3_fwd: Cout must be 64");
   if (D > 65535 || NB > 65535) return set_error("conv3d_cin1_k3_fwd: D / NB too large");
   const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH;
   dim3 grid(tiles_w * tiles_h, D, NB);
-  conv_cin1_k3_kernel<<<grid, 256, 0, stream>>>(x, w, D, H, W, tiles_w, tiles_h, y_raw, stats_partial);
+  conv_cin1_k3_kernel<<<grid, 256, 0, stream>>>(x, w, D, H, W, tiles_w, tiles_h, static_cast<__half*>(y_raw),
+                                                stats_partial);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -251,18 +260,21 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// eight channels of one voxel: relu((x-mean)*rstd)
-__device__ __forceinline__ void norm8(const float* __restrict__ src, const float (&mu)[8], const float (&rs)[8],
+// eight channels of one voxel (one 16-byte fp16 load): relu((x-mean)*rstd) in fp32
+__device__ __forceinline__ void norm8(const __half* __restrict__ src, const float (&mu)[8], const float (&rs)[8],
                                       float (&o)[8]) {
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
-  const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
-  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(src));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = fmaxf((x[i] - mu[i]) * rs[i], 0.f);
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h2[i]);
+    o[2 * i] = fmaxf((f.x - mu[2 * i]) * rs[2 * i], 0.f);
+    o[2 * i + 1] = fmaxf((f.y - mu[2 * i + 1]) * rs[2 * i + 1], 0.f);
+  }
 }
 
 __global__ void __launch_bounds__(256)
-in_relu_apply_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, long long voxels, int C,
+in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, long long voxels, int C,
                      __half* __restrict__ y, int y_ld, int y_coff) {
   const int nb = blockIdx.y;
   const int cg_per = C / 8;
@@ -286,7 +298,7 @@ in_relu_apply_kernel(const float* __restrict__ raw, const float* __restrict__ me
 }
 
 __global__ void __launch_bounds__(256)
-in_relu_pool_apply_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
+in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
                           int C, __half* __restrict__ y, int y_ld, int y_coff,
                           __half* __restrict__ pooled) {
   const int nb = blockIdx.y;
@@ -329,10 +341,11 @@ in_relu_pool_apply_kernel(const float* __restrict__ raw, const float* __restrict
   }
 }
 
-int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
+int in_relu_apply(const void* raw_v, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
                   int y_coff, void* pooled, cudaStream_t stream) {
   if (C % 8 || y_ld % 8 || y_coff % 8) return set_error("in_relu_apply: channel counts must be multiples of 8");
   if (NB > 65535) return set_error("in_relu_apply: NB too large");
+  const __half* raw = static_cast<const __half*>(raw_v);
   const int blocks = num_sms() * 8;
   if (pooled) {
     if ((D | H | W) & 1) return set_error("in_relu_apply: pooling needs even D, H, W");
@@ -350,7 +363,7 @@ int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H
 // ------------------------------------------------------------------------------------------------ head
 // 8 lanes per voxel, 8 channels per lane (C == 64): IN + ReLU + dot(w1) + b1, * w2 + b2, sigmoid.
 __global__ void __launch_bounds__(256)
-head_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, const float* __restrict__ hp, int D,
+head_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, const float* __restrict__ hp, int D,
             int H, int W, int crop, float* __restrict__ y) {
   constexpr int C = 64;
   const int nb = blockIdx.y;
@@ -394,12 +407,12 @@ head_kernel(const float* __restrict__ raw, const float* __restrict__ mean_rstd, 
   }
 }
 
-int head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* hp, int NB, int D, int H, int W,
+int head_1x1_sigmoid_fwd(const void* raw, const float* mean_rstd, const float* hp, int NB, int D, int H, int W,
                          int C, int crop, float* y, cudaStream_t stream) {
   if (C != 64) return set_error("head_1x1_sigmoid_fwd: C must be 64");
   if (crop < 0 || 2 * crop >= D || 2 * crop >= H || 2 * crop >= W) return set_error("head: bad crop");
   const int blocks = num_sms() * 8;
-  head_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, hp, D, H, W, crop, y);
+  head_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(static_cast<const __half*>(raw), mean_rstd, hp, D, H, W, crop, y);
   NC_CUDA(cudaGetLastError());
   return 0;
 }

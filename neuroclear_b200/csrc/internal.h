@@ -27,10 +27,11 @@ using TensorMapEncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, c
 TensorMapEncodeTiledFn get_tensor_map_encoder();
 
 // conv3d_tc.cu
+void debug_set_max_ctas(int n);
 int conv3d_k3_bn(int Cout);
 int conv3d_k3_td(int Cout);
 size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout);
-int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, float* y_raw,
+int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, void* y_raw,
                   float* stats_partial, cudaStream_t stream);
 int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, const float* bias,
                      int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream);
@@ -43,14 +44,14 @@ int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, con
                      int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
                      cudaStream_t stream);
 size_t conv_cin1_stats_tiles(int NB, int D, int H, int W);
-int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, float* y_raw,
+int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, void* y_raw,
                        float* stats_partial, cudaStream_t stream);
 size_t in_stats_scratch_bytes(int NB, int C);
 int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps, void* scratch,
                       float* mean_rstd, cudaStream_t stream);
-int in_relu_apply(const float* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
+int in_relu_apply(const void* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
                   int y_coff, void* pooled, cudaStream_t stream);
-int head_1x1_sigmoid_fwd(const float* raw, const float* mean_rstd, const float* hp, int NB, int D, int H, int W,
+int head_1x1_sigmoid_fwd(const void* raw, const float* mean_rstd, const float* hp, int NB, int D, int H, int W,
                          int C, int crop, float* y, cudaStream_t stream);
 int blend_gather_f32(const float* pieces, const long long* piece_off, const int* piece_z0, const int* padded,
                      const int* steps, int roi, int overlap, int out_z0, int out_nz, float* out, cudaStream_t stream);

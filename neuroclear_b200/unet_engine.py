@@ -3,15 +3,15 @@
 Data layout in HBM (per batch of NB cubes of D x H x W voxels, L0 = full, L1 = /2, L2 = /4 resolution):
 
     x      fp32 (NB, L0)            dice output / network input
-    raw0   fp32 (NB, L0, 64)        raw conv output of U1, U2, U12 (reused, consumed before rewritten)
+    raw0   fp16 (NB, L0, 64)        raw conv output of U1, U2, U12 (reused, consumed before rewritten)
     a1     fp16 (NB, L0, 64)        IN+ReLU(U1)
     cat1   fp16 (NB, L0, 128)       [IN+ReLU(U2) | t_conv1]          = torch.cat([conv1, t_conv1], 1)
     p1     fp16 (NB, L1, 64)        maxpool1
-    raw1   fp32 (NB, L1, 128)       raw output of U3, U4, U9, U10
+    raw1   fp16 (NB, L1, 128)       raw output of U3, U4, U9, U10
     a3     fp16 (NB, L1, 128)       IN+ReLU(U3) / (U9) / (U10)
     cat2   fp16 (NB, L1, 256)       [IN+ReLU(U4) | t_conv2]          = torch.cat([conv2, t_conv2], 1)
     p2     fp16 (NB, L2, 128)       maxpool2
-    raw2   fp32 (NB, L2, 256)       raw output of U5, U6, U7
+    raw2   fp16 (NB, L2, 256)       raw output of U5, U6, U7
     b1,b2  fp16 (NB, L2, 256)       bottom-layer ping-pong
     y      fp32 (NB, L0 - 2*crop)   sigmoid output, border already cut
 
@@ -101,9 +101,9 @@ class UnetDeconvEngine:
             lib.nc_conv3d_k3_stats_rows(128, nb, d // 4, h // 4, w // 4, 256) * 256,
         )
         ws = dict(
-            raw0=e(nb * l0 * 64, f32), a1=e(nb * l0 * 64, bf), cat1=e(nb * l0 * 128, bf), p1=e(nb * l1 * 64, bf),
-            raw1=e(nb * l1 * 128, f32), a3=e(nb * l1 * 128, bf), cat2=e(nb * l1 * 256, bf), p2=e(nb * l2 * 128, bf),
-            raw2=e(nb * l2 * 256, f32), b1=e(nb * l2 * 256, bf), b2=e(nb * l2 * 256, bf),
+            raw0=e(nb * l0 * 64, bf), a1=e(nb * l0 * 64, bf), cat1=e(nb * l0 * 128, bf), p1=e(nb * l1 * 64, bf),
+            raw1=e(nb * l1 * 128, bf), a3=e(nb * l1 * 128, bf), cat2=e(nb * l1 * 256, bf), p2=e(nb * l2 * 128, bf),
+            raw2=e(nb * l2 * 256, bf), b1=e(nb * l2 * 256, bf), b2=e(nb * l2 * 256, bf),
             stats=e(rows * 2, f32), mr=e(nb * 2 * 256, f32),
             fin=torch.zeros(lib.nc_in_stats_scratch_bytes(nb, 256), dtype=torch.uint8, device=dev),
         )

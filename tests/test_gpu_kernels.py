@@ -136,11 +136,11 @@ def test_first_layer_conv_and_stats(cuda, lib):
     wt = torch.randn((64, 1, 3, 3, 3), generator=g) * 0.3
     ref = F.conv3d(x, wt, padding=1)
     rows = lib.nc_conv3d_k3_stats_rows(1, nb, d, h, w, 64)
-    y = torch.empty((nb, d, h, w, 64), device=cuda)
+    y = torch.empty((nb, d, h, w, 64), dtype=torch.float16, device=cuda)
     st = torch.empty(rows * 2 * 64, device=cuda)
     xd, wd = x.to(cuda).contiguous(), wt.to(cuda).reshape(64, 27).contiguous()   # keep alive across the launch
     call("nc_conv3d_cin1_k3_fwd", ptr(xd), ptr(wd), nb, d, h, w, 64, ptr(y), ptr(st), stream_ptr())
-    assert torch.allclose(y.cpu(), _ndhwc(ref), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(y.cpu().float(), _ndhwc(ref), atol=1e-3, rtol=1e-3)    # fp32 math, fp16 storage
     mr = _finalize(lib, st, 1, nb, d, h, w, 64, cuda).cpu()
     mean = ref.mean(dim=(2, 3, 4))
     rstd = 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
@@ -160,12 +160,12 @@ def test_conv3d_k3_tensor_core(cuda, lib, cin, cout, nb, d, h, w):
     wd, xd = wt.to(cuda).contiguous(), _ndhwc(x).to(cuda)                        # keep alive across the launches
     call("nc_pack_weights_conv3d_k3", ptr(wd), cout, cin, ptr(packed), stream_ptr())
     rows = lib.nc_conv3d_k3_stats_rows(cin, nb, d, h, w, cout)
-    y = torch.full((nb, d, h, w, cout), float("nan"), device=cuda)
+    y = torch.full((nb, d, h, w, cout), float("nan"), dtype=torch.float16, device=cuda)
     st = torch.empty(rows * 2 * cout, device=cuda)
     call("nc_conv3d_k3_fwd", ptr(xd), nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
-    got = y.cpu()
+    got = y.cpu().float()
     assert torch.isfinite(got).all()
-    assert (got - _ndhwc(ref)).abs().max() <= 1e-3 * max(1.0, ref.abs().max().item())
+    assert (got - _ndhwc(ref)).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item())   # fp16 storage
     mr = _finalize(lib, st, cin, nb, d, h, w, cout, cuda).cpu()
     assert torch.allclose(mr[:, 0], ref.mean(dim=(2, 3, 4)), atol=2e-4)
     assert torch.allclose(mr[:, 1], 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5), rtol=2e-3)
@@ -195,14 +195,14 @@ def test_instance_norm_relu_pool_apply(cuda, lib, pool):
     from neuroclear_b200._lib import call, ptr, stream_ptr
     g = torch.Generator().manual_seed(2)
     nb, c, d, h, w = 2, 64, 4, 6, 8
-    raw = torch.randn((nb, c, d, h, w), generator=g) * 3 + 1
+    raw = (torch.randn((nb, c, d, h, w), generator=g) * 3 + 1).half().float()     # raw conv outputs are stored fp16
     mean = raw.mean(dim=(2, 3, 4))
     rstd = 1 / torch.sqrt(raw.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
     mr = torch.stack([mean, rstd], 1).contiguous().to(cuda)
     ref = F.relu((raw - mean[:, :, None, None, None]) * rstd[:, :, None, None, None])
     y = torch.zeros((nb, d, h, w, 2 * c), dtype=torch.float16, device=cuda)
     pooled = torch.zeros((nb, d // 2, h // 2, w // 2, c), dtype=torch.float16, device=cuda) if pool else None
-    rawd = _ndhwc(raw).to(cuda)
+    rawd = _ndhwc(raw).half().to(cuda)
     call("nc_in_relu_apply", ptr(rawd), ptr(mr), nb, d, h, w, c, ptr(y), 2 * c, c, ptr(pooled), stream_ptr())
     got = y.cpu().float()
     assert (got[..., :c] == 0).all()
@@ -215,7 +215,7 @@ def test_head_1x1_sigmoid_with_border_cut(cuda, lib):
     from neuroclear_b200._lib import call, ptr, stream_ptr
     g = torch.Generator().manual_seed(4)
     nb, c, d, h, w, crop = 2, 64, 10, 12, 14, 3
-    raw = torch.randn((nb, c, d, h, w), generator=g)
+    raw = torch.randn((nb, c, d, h, w), generator=g).half().float()
     mean = raw.mean(dim=(2, 3, 4))
     rstd = 1 / torch.sqrt(raw.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
     w1, b1 = torch.randn(c, generator=g) * 0.2, torch.tensor(0.05)
@@ -226,7 +226,7 @@ def test_head_1x1_sigmoid_with_border_cut(cuda, lib):
     mr = torch.stack([mean, rstd], 1).contiguous().to(cuda)
     for cr in (0, crop):
         y = torch.empty((nb, d - 2 * cr, h - 2 * cr, w - 2 * cr), device=cuda)
-        rawd = _ndhwc(raw).to(cuda)
+        rawd = _ndhwc(raw).half().to(cuda)
         call("nc_head_1x1_sigmoid_fwd", ptr(rawd), ptr(mr), ptr(hp), nb, d, h, w, c, cr, ptr(y), stream_ptr())
         want = ref[:, cr:d - cr, cr:h - cr, cr:w - cr]
         assert (y.cpu() - want).abs().max() <= 1e-5
