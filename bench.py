@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, nargs=3, default=[900, 900, 900])
-    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=9)   # 729 = 81 x 9: no ragged last batch
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     shape = tuple(args.size)

@@ -36,7 +36,7 @@ constexpr int pow2_at_least(int v) { return v <= 32 ? 32 : v <= 64 ? 64 : v <= 1
 // the kernel off the shared-memory-bandwidth roof an N = 64 MMA sits on (4 KB of A per 32 math cycles).  A tile is
 // TD = 4 output planes processed in two phases of three input planes; each phase walks all nine (kh,kw) weight
 // stages (192 rows = [kd2 | kd1 | kd0]), so the 6-slot plane ring always prefetches the next phase's planes.
-template <int KS, int BN, int TD, bool STACK = false>
+template <int KS, int BN, int TD, bool STACK = false, bool OUT_STAGE = false>
 struct ConvCfg {
   static constexpr int PAD = KS / 2;
   static constexpr int HALO_W = TW + KS - 1;
@@ -51,11 +51,12 @@ struct ConvCfg {
   static constexpr int STAGES_PER_CHUNK = STACK ? 2 * KS * KS : KS * KS * KS;
   static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4;  // barriers + per-warp stats scratch
   static constexpr int SMEM_LIMIT = 232448;
-  static constexpr int NBST_FIT = (SMEM_LIMIT - 1024 - AUX_BYTES - NSLOT * PLANE_BYTES) / BSTAGE_BYTES;
+  static constexpr int OUT_BYTES = OUT_STAGE ? 2 * 128 * 128 : 0;  // two 128-row x 64-channel fp16 store tiles
+  static constexpr int NBST_FIT = (SMEM_LIMIT - 1024 - AUX_BYTES - OUT_BYTES - NSLOT * PLANE_BYTES) / BSTAGE_BYTES;
   static constexpr int NBST = NBST_FIT > 8 ? 8 : NBST_FIT;
   static constexpr int ACC_COLS = TD * BN;
   static constexpr int TMEM_COLS = pow2_at_least(2 * ACC_COLS);
-  static constexpr int SMEM_BYTES = 1024 + NSLOT * PLANE_BYTES + NBST * BSTAGE_BYTES + AUX_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + NSLOT * PLANE_BYTES + NBST * BSTAGE_BYTES + OUT_BYTES + AUX_BYTES;
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(NBST >= 2, "weight ring too shallow");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "bad BN");
@@ -127,13 +128,15 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 template <int KS, int BN, int TD, int MODE, bool STACK>
 __global__ void __launch_bounds__(256, 1)
-conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs args) {
-  using C = ConvCfg<KS, BN, TD, STACK>;
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapOut,
+                 const ConvTcArgs args) {
+  using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + C::NSLOT * C::PLANE_BYTES;
-  uint8_t* aux = smB + C::NBST * C::BSTAGE_BYTES;
+  uint8_t* smOut = smB + C::NBST * C::BSTAGE_BYTES;  // 1024-aligned: every region is a multiple of 1 KB
+  uint8_t* aux = smOut + C::OUT_BYTES;
   uint64_t* planeFull = reinterpret_cast<uint64_t*>(aux);
   uint64_t* planeEmpty = planeFull + C::NSLOT;
   uint64_t* bFull = planeEmpty + C::NSLOT;
@@ -148,6 +151,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmapA);
+    if constexpr (MODE == 1) ptx::prefetch_tmap(&tmapOut);
     for (int i = 0; i < C::NSLOT; ++i) {
       ptx::mbar_init(&planeFull[i], 1);
       ptx::mbar_init(&planeEmpty[i], 1);
@@ -387,6 +391,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
     const int m = q * 32 + lane;  // accumulator row = voxel inside the tile plane
     const int mw = m & 7, mh = m >> 3;
     int it = 0;
+    [[maybe_unused]] int ost = 0;  // running index of output staging tiles (MODE 1)
     for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
       const TileCoord t = decode_tile(args, tile, TD);
       const int buf = it & 1;
@@ -401,8 +406,56 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
 #pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) csum[cc] = csq[cc] = 0.f;
 
+      if constexpr (MODE == 1) {
+        // Transposed conv: every (plane, 64-column group) = 128 coarse voxels x 64 channels of one tap is staged in
+        // shared memory as a swizzled 128 x 128 B tile and written by ONE TMA store whose tensor map walks the fine
+        // grid with element stride 2 in w and h (pixel shuffle); volume overhang is clipped by the TMA unit.
+        // (Per-thread 16-byte scatter stores cost one LSU wavefront each and made this kernel LSU-bound.)
+        const bool leader = threadIdx.x == 128;
 #pragma unroll 1
-      for (int j = 0; j < TD; ++j) {
+        for (int j = 0; j < TD; ++j) {
+          const int d = t.d0 + j;
+          if (d >= args.D) break;  // warp-uniform
+#pragma unroll 1
+          for (int g = 0; g < BN / 64; ++g) {
+            const int sb = ost & 1;
+            if (leader) ptx::bulk_wait_group_read<1>();  // the store that last used this staging tile has read it
+            ptx::named_bar_sync(2, 128);
+            uint8_t* stg = smOut + sb * (128 * 128) + m * 128;
+            const int n0 = t.n_tile * BN + g * 64;
+            const int tap = n0 / args.cout1;
+            const int co0 = n0 - tap * args.cout1;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t raw[32];
+              ptx::tmem_ld32(acc0 + j * BN + g * 64 + half * 32, raw);
+              ptx::tmem_ld_wait();
+              const float4* bp = reinterpret_cast<const float4*>(args.bias + co0 + half * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+                const uint4 pk = make_uint4(
+                    pack_half2_sat(__uint_as_float(raw[8 * i]) + b0.x, __uint_as_float(raw[8 * i + 1]) + b0.y),
+                    pack_half2_sat(__uint_as_float(raw[8 * i + 2]) + b0.z, __uint_as_float(raw[8 * i + 3]) + b0.w),
+                    pack_half2_sat(__uint_as_float(raw[8 * i + 4]) + b1.x, __uint_as_float(raw[8 * i + 5]) + b1.y),
+                    pack_half2_sat(__uint_as_float(raw[8 * i + 6]) + b1.z, __uint_as_float(raw[8 * i + 7]) + b1.w));
+                const int unit = half * 4 + i;
+                *reinterpret_cast<uint4*>(stg + ((unit ^ (m & 7)) << 4)) = pk;
+              }
+            }
+            ptx::fence_proxy_async();
+            ptx::named_bar_sync(2, 128);
+            if (leader) {
+              ptx::tma_store_5d(&tmapOut, smOut + sb * (128 * 128), args.coff1 + co0, 2 * t.w0 + (tap & 1),
+                                2 * t.h0 + ((tap >> 1) & 1), 2 * d + (tap >> 2), t.nb);
+              ptx::bulk_commit_group();
+            }
+            ++ost;
+          }
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; MODE == 0 && j < TD; ++j) {
         const int d = t.d0 + j;
         if (d >= args.D) break;  // warp-uniform
 #pragma unroll
@@ -432,31 +485,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
             }
             csum[cc] += warp_colsum32(v, lane);
             csq[cc] += warp_colsum32(v2, lane);
-          } else {
-            const int n0 = t.n_tile * BN + cc * 32;
-            const int tap = n0 / args.cout1;
-            const int co = n0 - tap * args.cout1;
-            if (valid_hw) {
-              const int od = 2 * d + (tap >> 2), oh = 2 * h + ((tap >> 1) & 1), ow = 2 * w + (tap & 1);
-              __half* dst =
-                  args.out_f16 +
-                  (((static_cast<size_t>(t.nb) * (2 * args.D) + od) * (2 * args.H) + oh) * (2 * args.W) + ow) *
-                      args.ld1 +
-                  args.coff1 + co;
-              const float* bp = args.bias + co;
-              uint4* dst4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float lo = __uint_as_float(raw[8 * i + 2 * e]) + __ldg(bp + 8 * i + 2 * e);
-                  const float hi = __uint_as_float(raw[8 * i + 2 * e + 1]) + __ldg(bp + 8 * i + 2 * e + 1);
-                  pk[e] = pack_half2_sat(lo, hi);
-                }
-                dst4[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              }
-            }
           }
         }
       }
@@ -482,6 +510,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
         }
         ptx::named_bar_sync(1, 128);
       }
+    }
+    if constexpr (MODE == 1) {
+      if (threadIdx.x == 128) ptx::bulk_wait_group_read<0>();  // shared memory must outlive the last TMA stores
     }
   }
 
@@ -556,11 +587,33 @@ static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, 
 static int g_max_ctas = 0;  // 0 = one CTA per SM
 void debug_set_max_ctas(int n) { g_max_ctas = n; }
 
+// Fine-grid output of the transposed conv: (ld, 2W, 2H, 2D, NB) fp16, box = 64 channels x 8 x 16 voxels taken with
+// element stride 2 in w and h (the bounding box is 16 x 32), SWIZZLE_128B shared-memory image.
+static int make_convT_out_tmap(CUtensorMap* m, const void* base, int ld, int W2, int H2, int D2, int NB) {
+  auto encode = get_tensor_map_encoder();
+  if (!encode) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[5] = {(cuuint64_t)ld, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)D2, (cuuint64_t)NB};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W2 * ld * 2, (cuuint64_t)H2 * W2 * ld * 2,
+                           (cuuint64_t)D2 * H2 * W2 * ld * 2};
+  cuuint32_t box[5] = {64, 2 * TW, 2 * TH, 1, 1};
+  cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (convT output) failed (%d)", (int)r);
+  return 0;
+}
+
 template <int KS, int BN, int TD, int MODE, bool STACK = false>
 static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
-  using C = ConvCfg<KS, BN, TD, STACK>;
-  CUtensorMap tm;
+  using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
+  CUtensorMap tm, tmo;
   if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H)) return rc;
+  if constexpr (MODE == 1) {
+    if (int rc = make_convT_out_tmap(&tmo, a.out_f16, a.ld1, 2 * a.W, 2 * a.H, 2 * a.D, a.NB)) return rc;
+  } else {
+    tmo = tm;
+  }
   a.tiles_w = (a.W + TW - 1) / TW;
   a.tiles_h = (a.H + TH - 1) / TH;
   a.tiles_d = (a.D + TD - 1) / TD;
@@ -573,7 +626,7 @@ static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream)
   }
   const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
   const int grid = a.total_tiles < cap ? a.total_tiles : cap;
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, a);
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, tmo, a);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -609,6 +662,8 @@ int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const 
                      int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream) {
   if (Cin % 64 || (8 * Cout) % 128 || Cout % 32) return set_error("convT3d_k2s2_fwd: unsupported channel counts");
   if (y_ld % 8 || y_coff % 8) return set_error("convT3d_k2s2_fwd: output slice must be 16-byte aligned");
+  if (Cout % 64) return set_error("convT3d_k2s2_fwd: Cout must be a multiple of 64");
+  if (reinterpret_cast<uintptr_t>(y) & 15) return set_error("convT3d_k2s2_fwd: output must be 16-byte aligned");
   ConvTcArgs a{};
   a.W = W, a.H = H, a.D = D, a.NB = NB;
   a.chunks = Cin / 64;

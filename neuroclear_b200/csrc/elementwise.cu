@@ -379,29 +379,38 @@ head_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd,
   const float b1 = __ldg(hp + C), w2 = __ldg(hp + C + 1), b2 = __ldg(hp + C + 2);
   const long long voxels = static_cast<long long>(D) * H * W;
   const int OD = D - 2 * crop, OH = H - 2 * crop, OW = W - 2 * crop;
-  // a warp handles 4 consecutive voxels per step; the loop bound is warp-uniform so the shuffles are safe
+  // a warp handles 4 consecutive voxels per step and two steps per iteration (two 16-byte loads in flight per
+  // lane); the loop bounds are warp-uniform so the shuffles are safe
   const long long warps_total = static_cast<long long>(gridDim.x) * 8;
-  for (long long q = blockIdx.x * 8ll + (threadIdx.x >> 5); q * 4 < voxels; q += warps_total) {
-    const long long vox = q * 4 + ((threadIdx.x & 31) >> 3);
-    const bool ok = vox < voxels;
-    const long long gv = static_cast<long long>(nb) * voxels + (ok ? vox : 0);
-    float o[8];
-    norm8(raw + gv * C + sub * 8, mu, rs, o);
-    float t = 0.f;
+  for (long long q = blockIdx.x * 8ll + (threadIdx.x >> 5); q * 4 < voxels; q += 2 * warps_total) {
+    long long vox[2];
+    bool ok[2];
+    float o[2][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t = fmaf(o[i], w1[i], t);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 4);
-    if (sub == 0 && ok) {
-      const int w = static_cast<int>(vox % W);
-      const long long r = vox / W;
-      const int h = static_cast<int>(r % H);
-      const int d = static_cast<int>(r / H);
-      const int od = d - crop, oh = h - crop, ow = w - crop;
-      if (od >= 0 && od < OD && oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
-        const float u = fmaf(w2, t + b1, b2);
-        y[((static_cast<long long>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-u));
+    for (int u = 0; u < 2; ++u) {
+      vox[u] = (q + u * warps_total) * 4 + ((threadIdx.x & 31) >> 3);
+      ok[u] = vox[u] < voxels;
+      const long long gv = static_cast<long long>(nb) * voxels + (ok[u] ? vox[u] : 0);
+      norm8(raw + gv * C + sub * 8, mu, rs, o[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = fmaf(o[u][i], w1[i], t);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      if (sub == 0 && ok[u]) {
+        const int w = static_cast<int>(vox[u] % W);
+        const long long r = vox[u] / W;
+        const int h = static_cast<int>(r % H);
+        const int d = static_cast<int>(r / H);
+        const int od = d - crop, oh = h - crop, ow = w - crop;
+        if (od >= 0 && od < OD && oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
+          const float uu = fmaf(w2, t + b1, b2);
+          y[((static_cast<long long>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-uu));
+        }
       }
     }
   }
