@@ -59,12 +59,14 @@ int nc_dice_extract_u16(const uint16_t* vol /*device*/, int32_t vol_z0, int32_t 
  * buffer is float32 [rows][2][Cout] (sum, sum of squares per tile). `cin` selects the kernel (1 = first layer). */
 int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cout);
 
-/* double_conv1.convolution.0 (networks.py:420,490): Conv3d(1 -> Cout, k3 s1 p1), fp32 CUDA-core direct conv.
- * x: float32 (NB,D,H,W); w: float32 (Cout,1,3,3,3) as stored in the state_dict; Cout must be 64.
- * y_raw: fp16 NDHWC (NB,D,H,W,Cout) WITHOUT bias (a bias in front of InstanceNorm(affine=False) cancels); the
- * statistics partials are taken from the fp32 values before the fp16 store. */
-int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d, int32_t h, int32_t wdt, int32_t cout,
-                          void* y_raw, float* stats_partial, nc_stream_t stream);
+/* double_conv1.convolution.0 (networks.py:420,490): Conv3d(1 -> 64, k3 s1 p1) on tcgen05 with an in-kernel im2col:
+ * every fp32 input is split into fp16 hi + lo parts (22 significant bits), K = 27 + 27 (+10 zero) = 64.
+ * nc_pack_weights_conv3d_cin1_k3: w float32 (64,1,3,3,3) as in the state_dict -> packed (8192 bytes, device).
+ * x: float32 (NB,D,H,W); y_raw: fp16 NDHWC (NB,D,H,W,64) WITHOUT bias (a bias in front of
+ * InstanceNorm(affine=False) cancels); statistics partials come from the fp32 accumulators. */
+int nc_pack_weights_conv3d_cin1_k3(const float* w, void* packed, nc_stream_t stream);
+int nc_conv3d_cin1_k3_fwd(const float* x, const void* packed, int32_t nb, int32_t d, int32_t h, int32_t wdt,
+                          int32_t cout, void* y_raw, float* stats_partial, nc_stream_t stream);
 
 /* Packed weight sizes / packing for the tensor-core kernels.  conv: w is OIDHW float32 (Cout,Cin,3,3,3);
  * convT: w is IODHW float32 (Cin,Cout,2,2,2) (torch ConvTranspose3d layout).  Output is the fp16 swizzled

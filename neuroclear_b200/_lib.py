@@ -24,6 +24,7 @@ SIGNATURES = {
     "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),
     "nc_dice_extract_u16": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),
     "nc_conv3d_k3_stats_rows": (i64, [i32, i32, i32, i32, i32, i32]),
+    "nc_pack_weights_conv3d_cin1_k3": (C.c_int, [vp, vp, vp]),
     "nc_conv3d_cin1_k3_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "nc_packed_weight_bytes": (i64, [i32, i32, i32]),
     "nc_pack_weights_conv3d_k3": (C.c_int, [vp, i32, i32, vp, vp]),

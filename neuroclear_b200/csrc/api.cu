@@ -49,9 +49,12 @@ int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, i
   return static_cast<int64_t>(conv3d_k3_stats_tiles(nb, d, h, w, cout));
 }
 
-int nc_conv3d_cin1_k3_fwd(const float* x, const float* w, int32_t nb, int32_t d, int32_t h, int32_t wdt, int32_t cout,
-                          void* y_raw, float* stats_partial, nc_stream_t stream) {
-  return conv3d_cin1_k3_fwd(x, w, nb, d, h, wdt, cout, y_raw, stats_partial, S(stream));
+int nc_pack_weights_conv3d_cin1_k3(const float* w, void* packed, nc_stream_t stream) {
+  return pack_conv1_weights(w, packed, S(stream));
+}
+int nc_conv3d_cin1_k3_fwd(const float* x, const void* packed, int32_t nb, int32_t d, int32_t h, int32_t wdt,
+                          int32_t cout, void* y_raw, float* stats_partial, nc_stream_t stream) {
+  return conv3d_cin1_k3_fwd(x, packed, nb, d, h, wdt, cout, y_raw, stats_partial, S(stream));
 }
 
 int64_t nc_packed_weight_bytes(int32_t cout, int32_t cin, int32_t transposed) {

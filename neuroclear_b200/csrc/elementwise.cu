@@ -1,4 +1,4 @@
-// Memory-bound kernels of the hot path: dice extraction, first-layer direct conv, InstanceNorm
+// Memory-bound kernels of the hot path: dice extraction, InstanceNorm
 // finalize/apply(+pool), the 1x1x1+sigmoid head, overlap blend, radix-select percentile, rescale/cast/crop and
 // the max-intensity projection.  All are coalesced, vectorised where the layout allows, and bit-exact where the
 // reference is integer / fixed-order fp32 arithmetic.  Reference citations are in include/neuroclear_b200.h.
@@ -57,112 +57,6 @@ int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, con
   dice_extract_kernel<<<grid, 256, 0, stream>>>(vol, vz0, vnz, size[0], size[1], size[2], padded[0], padded[1],
                                                 padded[2], steps[1], steps[2], roi - overlap, border, E, cube_begin,
                                                 cubes);
-  NC_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ first layer
-// Conv3d(1 -> 64, k3 p1) in fp32 on the CUDA cores.  Block = 8 warps on a 28(w) x 16(h) x 1(d) tile staged with its
-// halo in shared memory; a warp owns two h-rows, a lane two output channels (its 54 weights live in registers) and
-// walks the row in steps of 4 voxels: per (kd,kh) it broadcast-loads 6 inputs with one LDS.128 + one LDS.64 and
-// issues 24 FMAs.  Stores are fp16 pairs (128 B per voxel per warp), statistics come from the fp32 values.
-constexpr int C1_TW = 28, C1_TH = 16, C1_WSTEP = 4, C1_PITCH = 32;
-
-__global__ void __launch_bounds__(256)
-conv_cin1_k3_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int D, int H, int W, int tiles_w,
-                    int tiles_h, __half* __restrict__ y_raw, float* __restrict__ stats_partial) {
-  __shared__ __align__(16) float halo[3][C1_TH + 2][C1_PITCH];
-  __shared__ float red[8][2][64];
-  const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
-  const int d = blockIdx.y, nb = blockIdx.z;
-  const int w0 = tw * C1_TW, h0 = th * C1_TH;
-  const float* xin = x + static_cast<size_t>(nb) * D * H * W;
-  for (int i = threadIdx.x; i < 3 * (C1_TH + 2) * C1_PITCH; i += 256) {
-    const int ww = i % C1_PITCH;
-    const int hh = (i / C1_PITCH) % (C1_TH + 2);
-    const int dd = i / (C1_PITCH * (C1_TH + 2));
-    const int gz = d - 1 + dd, gy = h0 - 1 + hh, gx = w0 - 1 + ww;
-    float v = 0.f;
-    if (ww < C1_TW + 2 && gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = xin[(static_cast<size_t>(gz) * H + gy) * W + gx];
-    halo[dd][hh][ww] = v;
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float w0r[27], w1r[27];
-#pragma unroll
-  for (int t = 0; t < 27; ++t) {
-    w0r[t] = __ldg(wgt + (2 * lane) * 27 + t);
-    w1r[t] = __ldg(wgt + (2 * lane + 1) * 27 + t);
-  }
-  __syncthreads();
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 1
-  for (int rr = 0; rr < 2; ++rr) {
-    const int row = warp + 8 * rr;
-    const int h = h0 + row;
-    if (h >= H) break;
-#pragma unroll 1
-    for (int s = 0; s < C1_TW / C1_WSTEP; ++s) {
-      float acc0[C1_WSTEP], acc1[C1_WSTEP];
-#pragma unroll
-      for (int v = 0; v < C1_WSTEP; ++v) acc0[v] = acc1[v] = 0.f;
-#pragma unroll
-      for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const float4 a = *reinterpret_cast<const float4*>(&halo[kd][row + kh][s * C1_WSTEP]);
-          const float2 b = *reinterpret_cast<const float2*>(&halo[kd][row + kh][s * C1_WSTEP + 4]);
-          const float in[C1_WSTEP + 2] = {a.x, a.y, a.z, a.w, b.x, b.y};
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-            for (int v = 0; v < C1_WSTEP; ++v) {
-              acc0[v] = fmaf(in[v + kw], w0r[(kd * 3 + kh) * 3 + kw], acc0[v]);
-              acc1[v] = fmaf(in[v + kw], w1r[(kd * 3 + kh) * 3 + kw], acc1[v]);
-            }
-        }
-#pragma unroll
-      for (int v = 0; v < C1_WSTEP; ++v) {
-        const int w = w0 + s * C1_WSTEP + v;
-        if (w < W) {
-          __half2* dst = reinterpret_cast<__half2*>(
-              y_raw + ((((static_cast<size_t>(nb) * D + d) * H + h) * W + w) * 64 + 2 * lane));
-          *dst = __floats2half2_rn(fminf(fmaxf(acc0[v], -65504.f), 65504.f), fminf(fmaxf(acc1[v], -65504.f), 65504.f));
-          s0 += acc0[v];
-          s1 += acc1[v];
-          q0 = fmaf(acc0[v], acc0[v], q0);
-          q1 = fmaf(acc1[v], acc1[v], q1);
-        }
-      }
-    }
-  }
-  red[warp][0][2 * lane] = s0;
-  red[warp][0][2 * lane + 1] = s1;
-  red[warp][1][2 * lane] = q0;
-  red[warp][1][2 * lane + 1] = q1;
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][which][c];
-    const size_t row = (static_cast<size_t>(nb) * D + d) * gridDim.x + blockIdx.x;
-    stats_partial[(row * 2 + which) * 64 + c] = t;
-  }
-}
-
-size_t conv_cin1_stats_tiles(int NB, int D, int H, int W) {
-  return static_cast<size_t>(NB) * D * ((H + C1_TH - 1) / C1_TH) * ((W + C1_TW - 1) / C1_TW);
-}
-
-int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, void* y_raw,
-                       float* stats_partial, cudaStream_t stream) {
-  if (Cout != 64) return set_error("conv3d_cin1_k3_fwd: Cout must be 64");
-  if (D > 65535 || NB > 65535) return set_error("conv3d_cin1_k3_fwd: D / NB too large");
-  const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH;
-  dim3 grid(tiles_w * tiles_h, D, NB);
-  conv_cin1_k3_kernel<<<grid, 256, 0, stream>>>(x, w, D, H, W, tiles_w, tiles_h, static_cast<__half*>(y_raw),
-                                                stats_partial);
   NC_CUDA(cudaGetLastError());
   return 0;
 }

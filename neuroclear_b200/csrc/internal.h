@@ -44,7 +44,9 @@ int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, con
                      int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
                      cudaStream_t stream);
 size_t conv_cin1_stats_tiles(int NB, int D, int H, int W);
-int conv3d_cin1_k3_fwd(const float* x, const float* w, int NB, int D, int H, int W, int Cout, void* y_raw,
+// conv1_tc.cu
+int pack_conv1_weights(const float* w, void* packed, cudaStream_t stream);
+int conv3d_cin1_k3_fwd(const float* x, const void* wpacked, int NB, int D, int H, int W, int Cout, void* y_raw,
                        float* stats_partial, cudaStream_t stream);
 size_t in_stats_scratch_bytes(int NB, int C);
 int in_stats_finalize(const float* partial, int NB, long long rows, int C, long long voxels, float eps, void* scratch,

@@ -65,7 +65,9 @@ class UnetDeconvEngine:
         dev = self.device
         f = lambda k: sd[k].detach().to(dev, torch.float32).contiguous()
         with torch.cuda.device(dev):
-            self.w_first = f("double_conv1.convolution.0.weight").reshape(64, 27).contiguous()
+            w1 = f("double_conv1.convolution.0.weight").reshape(64, 27).contiguous()
+            self.w_first = torch.empty(8192, dtype=torch.uint8, device=dev)
+            call("nc_pack_weights_conv3d_cin1_k3", ptr(w1), ptr(self.w_first), stream_ptr())
             for prefix, cin, cout in _K3_LAYERS:
                 w = f(prefix + ".weight")
                 assert tuple(w.shape) == (cout, cin, 3, 3, 3), (prefix, tuple(w.shape))

@@ -139,12 +139,15 @@ def test_first_layer_conv_and_stats(cuda, lib):
     y = torch.empty((nb, d, h, w, 64), dtype=torch.float16, device=cuda)
     st = torch.empty(rows * 2 * 64, device=cuda)
     xd, wd = x.to(cuda).contiguous(), wt.to(cuda).reshape(64, 27).contiguous()   # keep alive across the launch
-    call("nc_conv3d_cin1_k3_fwd", ptr(xd), ptr(wd), nb, d, h, w, 64, ptr(y), ptr(st), stream_ptr())
-    assert torch.allclose(y.cpu().float(), _ndhwc(ref), atol=1e-3, rtol=1e-3)    # fp32 math, fp16 storage
+    packed = torch.empty(8192, dtype=torch.uint8, device=cuda)
+    call("nc_pack_weights_conv3d_cin1_k3", ptr(wd), ptr(packed), stream_ptr())
+    call("nc_conv3d_cin1_k3_fwd", ptr(xd), ptr(packed), nb, d, h, w, 64, ptr(y), ptr(st), stream_ptr())
+    ref_h = F.conv3d(x, wt.half().float(), padding=1)      # fp16 weights, hi+lo split input (~fp32), fp16 storage
+    assert torch.allclose(y.cpu().float(), _ndhwc(ref_h), atol=2e-3, rtol=2e-3)
     mr = _finalize(lib, st, 1, nb, d, h, w, 64, cuda).cpu()
     mean = ref.mean(dim=(2, 3, 4))
     rstd = 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
-    assert torch.allclose(mr[:, 0], mean, atol=1e-5) and torch.allclose(mr[:, 1], rstd, rtol=1e-4)
+    assert torch.allclose(mr[:, 0], mean, atol=1e-3) and torch.allclose(mr[:, 1], rstd, rtol=2e-3)
 
 
 @pytest.mark.parametrize("cin,cout,nb,d,h,w", [(64, 64, 1, 7, 20, 12), (64, 128, 2, 6, 10, 18), (128, 128, 1, 5, 17, 9),
