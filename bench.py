@@ -32,10 +32,14 @@ PUBLISHED_VOXELS_PER_S = 1.84e6   # 729 cubes at 1.84 it/s on t
 ROI, OVERLAP, BORDER = 120, 15, 10
 
 
-def synthetic_volume(shape, seed=0):
-    """uniform random uint16 volume (the reference's generator notebook is a missing blob)."""
-    rng = np.random.default_rng(seed)
-    return rng.integers(0, 65536, shape, dtype=np.uint16)
+def synthetic_volume(shape, seed=0, z0=0, z1=None):
+    """uniform random uint16 volume (the reference's generator notebook is a missing blob).
+    Seeded per z-plane, so a rank can generate exactly the planes [z0, z1) it owns without building the whole volume."""
+    z1 = shape[0] if z1 is None else z1
+    out = np.empty((z1 - z0, shape[1], shape[2]), dtype=np.uint16)
+    for z in range(z0, z1):
+        out[z - z0] = np.random.default_rng([seed, z]).integers(0, 65536, shape[1:], dtype=np.uint16)
+    return out
 
 
 def measured_peaks():
@@ -206,9 +210,9 @@ def main():
     plan = pipe.plan(shape)
     geo = plan["geo"]
     z0, z1 = plan["in_planes"]
-    # every rank generates the same volume and keeps only its planes (a real run would read its slab from disk)
-    vol_host = torch.from_numpy(synthetic_volume(shape)).pin_memory()
-    vol_dev = vol_host[z0:z1].to(dev)
+    # every rank generates (a real run would read from disk) only the input planes it needs
+    slab_host = torch.from_numpy(synthetic_volume(shape, z0=z0, z1=z1)).pin_memory()
+    vol_dev = slab_host.to(dev)
     o0, o1 = plan["out_planes"]
     out_host = torch.empty((o1 - o0, shape[1], shape[2]), dtype=torch.uint16).pin_memory()
 
@@ -235,7 +239,7 @@ def main():
         return ms, clocks, _lib.LAUNCHES - launches0, prof
 
     resident = lambda: pipe.run_device(vol_dev, z0, shape)
-    e2e = lambda: pipe.run(vol_host, out_host)
+    e2e = lambda: pipe.run_slab(slab_host, z0, shape, out_host)
 
     for _ in range(args.warmup):
         resident()

@@ -110,6 +110,22 @@ class DicedInference:
             queue = self.infer_cubes(vol_dev, vol_z0, plan)
             return self.assemble(queue, plan)
 
+    def run_slab(self, slab_host: torch.Tensor, slab_z0: int, size, out_host: torch.Tensor = None):
+        """Sharded entry point: `slab_host` holds only this rank's input planes plan(size)['in_planes'] of a (Z,Y,X)
+        volume (pinned uint16 host tensor).  H2D, the whole path and D2H of this rank's output slab."""
+        with torch.cuda.device(self.device):
+            plan = self.plan(tuple(size))
+            z0, z1 = plan["in_planes"]
+            if slab_z0 != z0 or slab_host.shape[0] != z1 - z0:
+                raise NeuroclearError("run_slab: expected input planes [%d, %d)" % (z0, z1))
+            vol_dev = slab_host.to(self.device, non_blocking=True)
+            out_dev = self.run_device(vol_dev, z0, tuple(size))
+            if out_host is None:
+                out_host = torch.empty(out_dev.shape, dtype=torch.uint16, pin_memory=True)
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_host.numpy(), plan["out_planes"]
+
     def run(self, volume, out_host: torch.Tensor = None):
         """volume: uint16 (Z,Y,X) numpy array or host tensor.  Returns (planes, (z_begin, z_end)): this rank's
         slab of the assembled uint16 volume as a host numpy array (the whole volume when not sharded)."""
