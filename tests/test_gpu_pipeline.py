@@ -157,3 +157,47 @@ def test_pure_padding_cubes_stay_finite(cuda):
     assert got.shape == vol.shape
     outs, blend, final, _ = _oracle_pipeline(vol, sd, roi, ov, bc, False)
     assert np.abs(got.astype(np.int64) - final.astype(np.int64)).max() <= 2e-2 * 65535 + 2
+
+
+def test_tiny_volume_single_cube(cuda):
+    """A volume smaller than one dice in every axis: pad_for_dicing makes exactly one 24^3 cube."""
+    from neuroclear_b200.pipeline import DicedInference
+    roi, ov, bc = 24, 6, 4
+    vol = (np.random.default_rng(8).random((5, 7, 9)) * 65535).astype(np.uint16)
+    sd = ounet.random_state_dict(seed=0, bias_std=0.1)
+    pipe = DicedInference(sd, cuda, roi, ov, bc, normalize_intensity=False, batch=2)
+    assert pipe.plan(vol.shape)["geo"].n_cubes == 1
+    got, _ = pipe.run(vol)
+    outs, blend, final, _ = _oracle_pipeline(vol, sd, roi, ov, bc, False)
+    assert got.shape == vol.shape and np.abs(got.astype(np.int64) - final.astype(np.int64)).max() <= 2e-2 * 65535 + 2
+
+
+def test_assembly_error_behaviour_matches_reference(cuda):
+    """Same guard rails as util/assemble_dice.py: wrong cube size asserts, border_cut 0 / overlap 0 are rejected
+    (the reference crashes / returns zeros for them), CPU tensors are refused (no fallback)."""
+    from neuroclear_b200._lib import NeuroclearError
+    from neuroclear_b200.dicing import Assemble_Dice, DiceImageDataSet
+    vol = np.zeros((40, 40, 40), dtype=np.uint16)
+    ds = DiceImageDataSet(_opt(24, 6, 4), volume=vol)
+    asm = Assemble_Dice(_opt(24, 6, 4), ds)
+    good = torch.zeros((1, 1, 32, 32, 32), device=cuda)
+    with pytest.raises(AssertionError):
+        asm.addToStack({"real": good, "fake": torch.zeros((1, 1, 30, 32, 32), device=cuda)})
+    with pytest.raises(NeuroclearError):
+        asm.addToStack({"real": good, "fake": good.cpu()})
+    with pytest.raises(KeyError):
+        asm.addToStack({"fake": good})                       # 'real' is required even with skip_real (:132-133)
+    with pytest.raises(NeuroclearError):
+        asm.assemble_all()                                   # queue not full
+    for _ in range(ds.geo.n_cubes):
+        asm.addToStack({"real": good, "fake": good})
+    with pytest.raises(NeuroclearError):
+        asm.addToStack({"real": good, "fake": good})         # more cubes than the volume has
+    asm.assemble_all()
+    assert asm.getDict()["fake"].shape == vol.shape and asm.getSnapshots(3, 0)["fake"].shape == (40, 40)
+    with pytest.raises(NeuroclearError):
+        Assemble_Dice(_opt(24, 6, 0), ds)
+    with pytest.raises(NeuroclearError):
+        Assemble_Dice(_opt(24, 0, 4), ds)
+    with pytest.raises(NeuroclearError):
+        DiceImageDataSet(_opt(24, 6, 4), volume=vol.astype(np.uint8))

@@ -1,6 +1,6 @@
 """Emulates the GPU path's rounding points on the CPU to size the operand-precision error vs the fp32 oracle."""
 import sys, numpy as np, torch, torch.nn.functional as F
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle import unet as ounet, dice, geometry as ogeo
 
 def rnd(t, dt):
@@ -36,19 +36,20 @@ def emu_forward(x, sd, dt, raw_dt=None):
 def psnr(a, b):
     return 10 * np.log10(1.0 / float(((a - b) ** 2).mean()))
 
-case = sys.argv[1]
-sd = ounet.random_state_dict(seed=0, bias_std=0.1)
-if case == 'small':
-    rng = np.random.default_rng(0); vol = (rng.random((40, 52, 30)) ** 3 * 65535).astype(np.uint16)
-    g = ogeo.dice_geometry(vol.shape, 24, 6, 4); cubes = range(g.n_cubes)
-elif case == 'c1':
-    rng = np.random.default_rng(4); vol = (rng.random((128, 128, 128)) ** 3 * 65535).astype(np.uint16)
-    g = ogeo.dice_geometry(vol.shape, 120, 15, 10); cubes = [int(c) for c in sys.argv[2:]] or [5]
-for i in cubes:
-    x = torch.from_numpy(dice.dice_cube_gather(vol, g, i))[None]
-    ref = ounet.unet_deconv_forward(x, sd)
-    res = []
-    for name, dt in (('bf16', torch.bfloat16), ('fp16', torch.float16)):
-        y = emu_forward(x, sd, dt)
-        res.append('%s max %.4f psnr %.1f' % (name, float((y - ref).abs().max()), psnr(y, ref)))
-    print('cube', i, 'zero-frac %.2f' % float((x == 0).float().mean()), ' | '.join(res), flush=True)
+if __name__ == "__main__":
+    case = sys.argv[1]
+    sd = ounet.random_state_dict(seed=0, bias_std=0.1)
+    if case == 'small':
+        rng = np.random.default_rng(0); vol = (rng.random((40, 52, 30)) ** 3 * 65535).astype(np.uint16)
+        g = ogeo.dice_geometry(vol.shape, 24, 6, 4); cubes = range(g.n_cubes)
+    elif case == 'c1':
+        rng = np.random.default_rng(4); vol = (rng.random((128, 128, 128)) ** 3 * 65535).astype(np.uint16)
+        g = ogeo.dice_geometry(vol.shape, 120, 15, 10); cubes = [int(c) for c in sys.argv[2:]] or [5]
+    for i in cubes:
+        x = torch.from_numpy(dice.dice_cube_gather(vol, g, i))[None]
+        ref = ounet.unet_deconv_forward(x, sd)
+        res = []
+        for name, dt in (('bf16', torch.bfloat16), ('fp16', torch.float16)):
+            y = emu_forward(x, sd, dt)
+            res.append('%s max %.4f psnr %.1f' % (name, float((y - ref).abs().max()), psnr(y, ref)))
+        print('cube', i, 'zero-frac %.2f' % float((x == 0).float().mean()), ' | '.join(res), flush=True)
