@@ -2,13 +2,16 @@
 //
 // With one input channel the GEMM K is only 27, so there is nothing for TMA to stage: the A operand is built in the
 // kernel (im2col).  To keep fp32 fidelity of the 16-bit input on fp16 tensor cores every input value x is split
-// into hi = fp16(x) and lo = fp16(x - hi) (22 significant bits together); K = 27 (hi) + 27 (lo) + 10 (zero) = 64
-// = ONE 128-byte swizzled row per voxel, and the weight matrix simply repeats the 27 taps for the lo half.
+// into hi = fp16(x) and lo = fp16(x - hi) (22 significant bits together); K index = 2*tap + {0: hi, 1: lo}, i.e.
+// 27 (hi,lo) words + 5 zero words = 64 halves = ONE 128-byte swizzled row per voxel, and the weight matrix simply
+// holds every tap twice.  The split is done ONCE per halo element (when the halo is staged in shared memory as
+// packed half2 words), so building a voxel's K-row is 27 word loads and 8 vector stores.
 //
 //   warps 4-7  producers: per 8(w) x 16(h) x 1(d) tile load the 10 x 18 x 3 fp32 halo into shared memory, then each
 //              thread gathers its voxel's 27 neighbours, splits, and writes its 128-byte K-row (SWIZZLE_128B image);
 //              fence.proxy.async + mbarrier hand the stage to the tensor core
-//   warp  8    TMEM allocation, weight load (8 KB, resident for the whole kernel), MMA issue: 4 x (128x64x16)
+//   warp  4    additionally: TMEM allocation, weight load (8 KB, resident for the whole kernel) and, once a stage is
+//              complete, the MMA issue: 4 x (128x64x16)
 //   warps 0-3  epilogue: TMEM -> registers; per-channel sum / sum-of-squares kept in registers across ALL tiles of a
 //              cube (one butterfly reduction per cube per CTA instead of per tile); fp16 tile staged in shared memory
 //              and written with one TMA store (volume overhang clipped by the TMA unit)
@@ -31,8 +34,8 @@ constexpr int NACC = 8;                          // accumulator ring (8 x 64 TME
 constexpr int A_BYTES = 128 * 128;               // 128 voxels x 64 halves
 constexpr int B_BYTES = 64 * 128;
 constexpr int OUT_BYTES = 128 * 128;
-constexpr int THREADS = 288;
-constexpr int SMEM_BYTES = 1024 + NA * A_BYTES + B_BYTES + 2 * OUT_BYTES + NA * HALO_PITCH * 4 + 4 * 2 * 64 * 4 + 1024;
+constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = NA * A_BYTES + B_BYTES + 2 * OUT_BYTES + NA * HALO_PITCH * 4 + 4 * 2 * 64 * 4 + 1024;
 }  // namespace c1
 
 struct Conv1Args {
@@ -65,8 +68,9 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 __global__ void __launch_bounds__(c1::THREADS, 1)
 conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args args) {
   using namespace c1;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // __align__(1024) instead of rounding the pointer up by hand: an integer round trip makes the compiler forget the
+  // address space and emit generic LD/ST for every shared-memory access
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smA = smem;
   uint8_t* smB = smA + NA * A_BYTES;
   uint8_t* smOut = smB + B_BYTES;
@@ -83,7 +87,6 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmapOut);
     for (int i = 0; i < NA; ++i) {
-      ptx::mbar_init(&aFull[i], 128);
       ptx::mbar_init(&aEmpty[i], 1);
     }
     for (int i = 0; i < NACC; ++i) {
@@ -93,20 +96,27 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
     ptx::mbar_init(bFull, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == 4) {
     ptx::tmem_alloc<512>(tmemPtr);
     ptx::tmem_relinquish();
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bFull, B_BYTES);
+      ptx::bulk_load(smB, args.wpacked, B_BYTES, bFull);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmemPtr;
-  const int total_tiles = args.NB * args.tiles_per_cube;
 
   if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ im2col producers
     const int pt = threadIdx.x - 128;  // 0..127 = GEMM row = voxel of the tile
     const int mw = pt & 7, mh = pt >> 3;
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_lo = ((ptx::smem_u32(smB) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t smA_u32 = ptx::smem_u32(smA);
     constexpr int NPRE = (HALO_FLOATS + 127) / 128;  // halo elements per thread (5)
     // halo element e of this thread: index i = pt + 128 e -> (dd, hh, ww), fixed for the whole kernel
     int off_d[NPRE], off_h[NPRE], off_w[NPRE];
@@ -138,10 +148,13 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
     for (int it = 0; have; ++it) {
       const int st = it & (NA - 1);
       ptx::mbar_wait(&aEmpty[st], ((it / NA) & 1) ^ 1);
-      float* hl = halo + st * HALO_PITCH;
+      uint32_t* hl = reinterpret_cast<uint32_t*>(halo) + st * HALO_PITCH;
 #pragma unroll
       for (int e = 0; e < NPRE; ++e)
-        if (pt + 128 * e < HALO_FLOATS) hl[pt + 128 * e] = pre[e];
+        if (pt + 128 * e < HALO_FLOATS) {
+          const __half h = __float2half_rn(pre[e]);
+          hl[pt + 128 * e] = pack_h2(h, __float2half_rn(pre[e] - __half2float(h)));   // (hi, lo)
+        }
       // advance to the next tile of this CTA (tiles of cube nb, then cube nb+1, ...) and start its loads
       tile += gridDim.x;
       if (tile >= args.tiles_per_cube) {
@@ -152,66 +165,42 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
       if (have) fetch(nb, tile, pre);
       {
         ptx::named_bar_sync(3, 128);
-        __half hi[27], lo[27];
+        uint32_t kw32[32];  // the voxel's K-row: word t = (hi, lo) of tap t, words 27..31 zero
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const float v = hl[(kd * HH + mh + kh) * HW + mw + kw];
-              const __half h = __float2half_rn(v);
-              hi[(kd * 3 + kh) * 3 + kw] = h;
-              lo[(kd * 3 + kh) * 3 + kw] = __float2half_rn(v - __half2float(h));
-            }
-        // K layout: [0,27) hi taps, [27,54) lo taps, [54,64) zero; eight 16-byte units of 8 halves
+            for (int kw = 0; kw < 3; ++kw) kw32[(kd * 3 + kh) * 3 + kw] = hl[(kd * HH + mh + kh) * HW + mw + kw];
+#pragma unroll
+        for (int t = 27; t < 32; ++t) kw32[t] = 0u;
         uint8_t* row = smA + st * A_BYTES + pt * 128;
-        const __half z = __float2half_rn(0.f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          __half e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = u * 8 + i;
-            e[i] = k < 27 ? hi[k < 27 ? k : 0] : (k < 54 ? lo[k < 54 ? k - 27 : 0] : z);
-          }
+        for (int u = 0; u < 8; ++u)
           *reinterpret_cast<uint4*>(row + ((u ^ (pt & 7)) << 4)) =
-              make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-        }
+              make_uint4(kw32[4 * u], kw32[4 * u + 1], kw32[4 * u + 2], kw32[4 * u + 3]);
         ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
-        ptx::mbar_arrive(&aFull[st]);
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ weights + MMA issue
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(bFull, B_BYTES);
-      ptx::bulk_load(smB, args.wpacked, B_BYTES, bFull);
-    }
-    ptx::mbar_wait(bFull, 0);
-    constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64);
-    constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t b_lo = ((ptx::smem_u32(smB) >> 4) & 0x3FFF) | (1u << 16);
-    const uint32_t smA_u32 = ptx::smem_u32(smA);
-    const int my_tiles = args.NB * ((args.tiles_per_cube - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                    static_cast<int>(gridDim.x));
-    for (int it = 0; it < my_tiles; ++it) {
-      const int st = it & (NA - 1), slot = it & (NACC - 1);
-      ptx::mbar_wait(&accEmpty[slot], ((it / NACC) & 1) ^ 1);
-      ptx::mbar_wait(&aFull[st], (it / NA) & 1);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t a_lo = (((smA_u32 + st * A_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+        ptx::named_bar_sync(3, 128);  // the whole stage is written and fenced
+        if (warp == 4) {
+          // producer warp 4 doubles as the MMA issuer (8 warps keep the register cap at 255: the epilogue holds
+          // 128 running statistics per thread)
+          const int slot = it & (NACC - 1);
+          if (it == 0) ptx::mbar_wait(bFull, 0);
+          ptx::mbar_wait(&accEmpty[slot], ((it / NACC) & 1) ^ 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t a_lo = (((smA_u32 + st * A_BYTES) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_f16(tmem_base + slot * 64, (static_cast<uint64_t>(HI) << 32) | (a_lo + 2 * k),
-                        (static_cast<uint64_t>(HI) << 32) | (b_lo + 2 * k), idesc, k == 0 ? 0u : 1u);
-        ptx::umma_commit(&aEmpty[st]);
-        ptx::umma_commit(&accFull[slot]);
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(tmem_base + slot * 64, (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2 * k),
+                            (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + 2 * k), idesc, k == 0 ? 0u : 1u);
+            ptx::umma_commit(&aEmpty[st]);
+            ptx::umma_commit(&accFull[slot]);
+          }
+          __syncwarp();
+        }
       }
-      __syncwarp();
     }
-    (void)total_tiles;
   } else if (warp < 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp;  // TMEM lane quarter
@@ -249,7 +238,7 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a = __uint_as_float(raw[8 * i + 2 * e]), b = __uint_as_float(raw[8 * i + 2 * e + 1]);
-              __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+              __half2 t = __floats2half2_rn(a, b);  // |sum_27 w*x|, x in [0,1]: far inside the fp16 range
               pk[e] = *reinterpret_cast<uint32_t*>(&t);
             }
             *reinterpret_cast<uint4*>(stg + (((c * 4 + i) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -293,18 +282,18 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
 }
 
-// weights: OIDHW fp32 (64,1,3,3,3) -> 64 rows x 64 halves, k<27: w[co][k], 27<=k<54: w[co][k-27], else 0; swizzled
+// weights: OIDHW fp32 (64,1,3,3,3) -> 64 rows x 64 halves, k = 2*tap + {0,1}: w[co][tap] (k >= 54: 0); swizzled
 __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __half* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 64 * 64) return;
   const int r = idx >> 6, k = idx & 63;
-  const float v = k < 27 ? w[r * 27 + k] : (k < 54 ? w[r * 27 + k - 27] : 0.f);
+  const float v = k < 54 ? w[r * 27 + (k >> 1)] : 0.f;
   out[r * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7))] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
 }
 

@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapOut,
                  const ConvTcArgs args) {
   using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // __align__(1024), not a hand-rounded pointer: an integer round trip makes the compiler forget the address space
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smA = smem;
   uint8_t* smB = smem + C::NSLOT * C::PLANE_BYTES;
   uint8_t* smOut = smB + C::NBST * C::BSTAGE_BYTES;  // 1024-aligned: every region is a multiple of 1 KB
