@@ -171,11 +171,11 @@ __global__ void __launch_bounds__(256)
 in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, long long voxels, int C,
                      __half* __restrict__ y, int y_ld, int y_coff) {
   const int nb = blockIdx.y;
-  const int cg_per = C / 8;
-  const long long total = voxels * cg_per;
+  const unsigned cg_per = C / 8;
+  const unsigned total = static_cast<unsigned>(voxels) * cg_per;  // per cube: < 2^31 (checked by the launcher)
   const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
-  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
-    const long long vox = idx / cg_per;
+  for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const unsigned vox = idx / cg_per;
     const int cg = static_cast<int>(idx - vox * cg_per);
     float mu[8], rs[8], o[8];
 #pragma unroll
@@ -198,11 +198,11 @@ in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restric
   const int nb = blockIdx.y;
   const int cg_per = C / 8;
   const int PD = D / 2, PH = H / 2, PW = W / 2;
-  const long long total = static_cast<long long>(PD) * PH * PW * cg_per;
+  const unsigned total = static_cast<unsigned>(PD) * PH * PW * cg_per;  // per cube: < 2^31 (checked by the launcher)
   const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
-  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+  for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
     const int cg = static_cast<int>(idx % cg_per);
-    long long r = idx / cg_per;
+    unsigned r = idx / cg_per;
     const int pw = static_cast<int>(r % PW);
     r /= PW;
     const int ph = static_cast<int>(r % PH);
@@ -239,6 +239,7 @@ int in_relu_apply(const void* raw_v, const float* mean_rstd, int NB, int D, int 
                   int y_coff, void* pooled, cudaStream_t stream) {
   if (C % 8 || y_ld % 8 || y_coff % 8) return set_error("in_relu_apply: channel counts must be multiples of 8");
   if (NB > 65535) return set_error("in_relu_apply: NB too large");
+  if (static_cast<long long>(D) * H * W * (C / 8) >= (1ll << 31)) return set_error("in_relu_apply: cube too large");
   const __half* raw = static_cast<const __half*>(raw_v);
   const int blocks = num_sms() * 8;
   if (pooled) {
@@ -271,20 +272,20 @@ head_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd,
     w1[i] = __ldg(hp + sub * 8 + i);
   }
   const float b1 = __ldg(hp + C), w2 = __ldg(hp + C + 1), b2 = __ldg(hp + C + 2);
-  const long long voxels = static_cast<long long>(D) * H * W;
+  const unsigned voxels = static_cast<unsigned>(D) * H * W;  // per cube: < 2^29 (checked by the launcher)
   const int OD = D - 2 * crop, OH = H - 2 * crop, OW = W - 2 * crop;
   // a warp handles 4 consecutive voxels per step and two steps per iteration (two 16-byte loads in flight per
   // lane); the loop bounds are warp-uniform so the shuffles are safe
-  const long long warps_total = static_cast<long long>(gridDim.x) * 8;
-  for (long long q = blockIdx.x * 8ll + (threadIdx.x >> 5); q * 4 < voxels; q += 2 * warps_total) {
-    long long vox[2];
+  const unsigned warps_total = gridDim.x * 8u;
+  for (unsigned q = blockIdx.x * 8u + (threadIdx.x >> 5); q * 4 < voxels; q += 2 * warps_total) {
+    unsigned vox[2];
     bool ok[2];
     float o[2][8];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       vox[u] = (q + u * warps_total) * 4 + ((threadIdx.x & 31) >> 3);
       ok[u] = vox[u] < voxels;
-      const long long gv = static_cast<long long>(nb) * voxels + (ok[u] ? vox[u] : 0);
+      const size_t gv = static_cast<size_t>(nb) * voxels + (ok[u] ? vox[u] : 0u);
       norm8(raw + gv * C + sub * 8, mu, rs, o[u]);
     }
 #pragma unroll
@@ -297,13 +298,13 @@ head_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd,
       t += __shfl_xor_sync(0xffffffffu, t, 4);
       if (sub == 0 && ok[u]) {
         const int w = static_cast<int>(vox[u] % W);
-        const long long r = vox[u] / W;
+        const unsigned r = vox[u] / W;
         const int h = static_cast<int>(r % H);
         const int d = static_cast<int>(r / H);
         const int od = d - crop, oh = h - crop, ow = w - crop;
         if (od >= 0 && od < OD && oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
           const float uu = fmaf(w2, t + b1, b2);
-          y[((static_cast<long long>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-uu));
+          y[((static_cast<size_t>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-uu));
         }
       }
     }
@@ -314,6 +315,7 @@ int head_1x1_sigmoid_fwd(const void* raw, const float* mean_rstd, const float* h
                          int C, int crop, float* y, cudaStream_t stream) {
   if (C != 64) return set_error("head_1x1_sigmoid_fwd: C must be 64");
   if (crop < 0 || 2 * crop >= D || 2 * crop >= H || 2 * crop >= W) return set_error("head: bad crop");
+  if (static_cast<long long>(D) * H * W >= (1ll << 29)) return set_error("head: cube too large");
   const int blocks = num_sms() * 8;
   head_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(static_cast<const __half*>(raw), mean_rstd, hp, D, H, W, crop, y);
   NC_CUDA(cudaGetLastError());

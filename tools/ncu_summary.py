@@ -6,7 +6,8 @@ rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 want = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "ms"), ("dram__bytes_read.sum", "dram_rd"),
-        ("dram__bytes_write.sum", "dram_wr"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("dram__bytes_write.sum", "dram_wr"), ("dram__bytes_read.sum.per_second", "rd/s"),
+        ("dram__bytes_write.sum.per_second", "wr/s"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
         ("sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "hmma%"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
