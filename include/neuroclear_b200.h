@@ -76,18 +76,23 @@ int nc_pack_weights_conv3d_k3(const float* w_oidhw, int32_t cout, int32_t cin, v
 int nc_pack_weights_convT3d_k2s2(const float* w_iodhw, int32_t cin, int32_t cout, void* packed, nc_stream_t stream);
 
 /* nn.Conv3d(Cin -> Cout, k3 s1 p1) of double_conv / triple_conv / last_conv (networks.py:413-476): tcgen05
- * implicit GEMM, fp16 operands, fp32 accumulate.  x: fp16 NDHWC (NB,D,H,W,Cin) (Cin may be a concat buffer);
+ * implicit GEMM, fp16 operands, fp32 accumulate.  x: fp16 NDHWC (NB,D,H,W,Cin) (Cin may be a concat buffer).
+ * in_mean_rstd == NULL: x is the conv's input as is (already normalised activations).
+ * in_mean_rstd != NULL (float32 (NB,2,Cin) from nc_in_stats_finalize): x is the RAW output of the previous conv
+ *   and the InstanceNorm + ReLU between the two layers (networks.py:422-423 etc.) is applied inside this kernel
+ *   while the input planes sit in shared memory — no separate nc_in_relu_apply pass.
  * y_raw: fp16 NDHWC (NB,D,H,W,Cout) without bias; stats_partial (from the fp32 accumulators) as above.
  * Cin % 64 == 0, Cout in {64,128k}. */
-int nc_conv3d_k3_fwd(const void* x_f16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
-                     int32_t cout, void* y_raw, float* stats_partial, nc_stream_t stream);
+int nc_conv3d_k3_fwd(const void* x_f16, const float* in_mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+                     int32_t cin, const void* packed, int32_t cout, void* y_raw, float* stats_partial,
+                     nc_stream_t stream);
 
 /* nn.ConvTranspose3d(Cin -> Cout, k2 s2) t_conv2 / t_conv1 (networks.py:500,503) fused with the channel concat
  * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as fp16 into
  * channels [y_coff, y_coff+Cout) of an NDHWC buffer (NB,2D,2H,2W,y_ld). */
-int nc_convT3d_k2s2_fwd(const void* x_f16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
-                        const void* packed, const float* bias, int32_t cout, void* y_f16, int32_t y_ld,
-                        int32_t y_coff, nc_stream_t stream);
+int nc_convT3d_k2s2_fwd(const void* x_f16, const float* in_mean_rstd /* as for nc_conv3d_k3_fwd */, int32_t nb,
+                        int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed, const float* bias,
+                        int32_t cout, void* y_f16, int32_t y_ld, int32_t y_coff, nc_stream_t stream);
 
 /* InstanceNorm3d(affine=False, eps) statistics (networks.py:33-34): deterministic fixed-order two-level reduction
  * of the per-tile partials in fp64 -> mean_rstd float32 (NB, 2, C): [:,0,:] = mean, [:,1,:] = 1/sqrt(var_biased+eps).

@@ -29,8 +29,8 @@ SIGNATURES = {
     "nc_packed_weight_bytes": (i64, [i32, i32, i32]),
     "nc_pack_weights_conv3d_k3": (C.c_int, [vp, i32, i32, vp, vp]),
     "nc_pack_weights_convT3d_k2s2": (C.c_int, [vp, i32, i32, vp, vp]),
-    "nc_conv3d_k3_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
-    "nc_convT3d_k2s2_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
+    "nc_conv3d_k3_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
+    "nc_convT3d_k2s2_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
     "nc_in_stats_scratch_bytes": (i64, [i32, i32]),
     "nc_in_stats_finalize": (C.c_int, [vp, i32, i64, i32, i64, f32, vp, vp, vp]),
     "nc_in_relu_apply": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),

@@ -67,13 +67,15 @@ int nc_pack_weights_convT3d_k2s2(const float* w, int32_t cin, int32_t cout, void
   return pack_weights(w, packed, cout, cin, 8, 1, S(stream));
 }
 
-int nc_conv3d_k3_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
-                     int32_t cout, void* y_raw, float* stats_partial, nc_stream_t stream) {
-  return conv3d_k3_fwd(x, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, S(stream));
+int nc_conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+                     int32_t cin, const void* packed, int32_t cout, void* y_raw, float* stats_partial,
+                     nc_stream_t stream) {
+  return conv3d_k3_fwd(x, in_mean_rstd, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, S(stream));
 }
-int nc_convT3d_k2s2_fwd(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin, const void* packed,
-                        const float* bias, int32_t cout, void* y, int32_t y_ld, int32_t y_coff, nc_stream_t stream) {
-  return convT3d_k2s2_fwd(x, nb, d, h, w, cin, packed, bias, cout, y, y_ld, y_coff, S(stream));
+int nc_convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+                        int32_t cin, const void* packed, const float* bias, int32_t cout, void* y, int32_t y_ld,
+                        int32_t y_coff, nc_stream_t stream) {
+  return convT3d_k2s2_fwd(x, in_mean_rstd, nb, d, h, w, cin, packed, bias, cout, y, y_ld, y_coff, S(stream));
 }
 
 int64_t nc_in_stats_scratch_bytes(int32_t nb, int32_t c) { return static_cast<int64_t>(in_stats_scratch_bytes(nb, c)); }

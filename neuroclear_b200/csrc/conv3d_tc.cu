@@ -66,6 +66,9 @@ struct ConvCfg {
 struct ConvTcArgs {
   int W, H, D, NB;
   int max_ctas;  // persistent grid size cap (debug hook: forces several tiles per CTA on small problems)
+  // XF: the input is a RAW conv output; InstanceNorm + ReLU of the producer layer are applied on the fly
+  const float* in_mr;  // [NB][2][cin_total]: mean, rstd of the input's channels
+  int cin_total;
   int chunks;  // Cin / 64
   int n_tiles;  // GEMM N / BN
   int tiles_w, tiles_h, tiles_d;
@@ -126,8 +129,13 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int KS, int BN, int TD, int MODE, bool STACK>
-__global__ void __launch_bounds__(256, 1)
+// XF (fused InstanceNorm-apply + ReLU of the PREVIOUS layer): the TMA producer stages the previous layer's RAW fp16
+// output; four extra warps (8..11) rewrite every landed halo plane in place — relu((x - mean) * rstd) in fp32, back
+// to fp16 — before handing it to the MMA warp.  Rows outside the volume were zero-filled by TMA and are left
+// untouched, which is exactly the conv's zero padding of the NORMALISED tensor.  This removes the separate
+// read-raw / write-normalised pass between two convolutions.
+template <int KS, int BN, int TD, int MODE, bool STACK, bool XF>
+__global__ void __launch_bounds__(XF ? 384 : 256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapOut,
                  const ConvTcArgs args) {
   using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
@@ -143,7 +151,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   uint64_t* bEmpty = bFull + C::NBST;
   uint64_t* accFull = bEmpty + C::NBST;
   uint64_t* accEmpty = accFull + 2;
-  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(accEmpty + 2);
+  uint64_t* planeReady = accEmpty + 2;  // XF only: plane transformed, MMA may read it
+  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(planeReady + C::NSLOT);
   float* statScratch = reinterpret_cast<float*>(aux + 1024);  // [4 warps][2][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -155,6 +164,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     for (int i = 0; i < C::NSLOT; ++i) {
       ptx::mbar_init(&planeFull[i], 1);
       ptx::mbar_init(&planeEmpty[i], 1);
+      ptx::mbar_init(&planeReady[i], 1);
     }
     for (int i = 0; i < C::NBST; ++i) {
       ptx::mbar_init(&bFull[i], 1);
@@ -262,7 +272,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                 s -= C::NSLOT;
                 p ^= 1;
               }
-              ptx::mbar_wait(&planeFull[s], p);
+              ptx::mbar_wait(XF ? &planeReady[s] : &planeFull[s], p);
             }
             ptx::tc_fence_after();
             for (int khw = 0; khw < 9; ++khw) {
@@ -330,7 +340,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                 s -= C::NSLOT;
                 p ^= 1;
               }
-              ptx::mbar_wait(&planeFull[s], p);
+              ptx::mbar_wait(XF ? &planeReady[s] : &planeFull[s], p);
             }
             ptx::tc_fence_after();
             for (int khw = 0; khw < KS * KS; ++khw) {
@@ -385,7 +395,58 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (XF && warp >= 8) {
+    // ------------------------------------------------------------ in-place InstanceNorm + ReLU of landed planes
+    const int tt = threadIdx.x - 256;  // 0..127
+    const int g = tt & 7;              // logical 16-byte unit = channels [8g, 8g+8) of the chunk
+    const int r0 = tt >> 3;            // rows r0, r0+16, ...
+    int slot = 0;
+    uint32_t ph = 0;
+    for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
+      const TileCoord t = decode_tile(args, tile, TD);
+      for (int c = 0; c < args.chunks; ++c) {
+        float mu[8], rs[8];
+        const float* mr = args.in_mr + static_cast<size_t>(t.nb) * 2 * args.cin_total + c * 64 + g * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          mu[i] = __ldg(mr + i);
+          rs[i] = __ldg(mr + args.cin_total + i);
+        }
+        for (int i = 0; i < C::PPC; ++i) {
+          const int d = t.d0 - C::PAD + i;
+          const bool plane_valid = d >= 0 && d < args.D;
+          ptx::mbar_wait(&planeFull[slot], ph);
+          uint8_t* pl = smA + slot * C::PLANE_BYTES;
+          if (plane_valid) {
+#pragma unroll 4
+            for (int row = r0; row < C::PLANE_ROWS; row += 16) {
+              const int hh = row / C::HALO_W, ww = row - hh * C::HALO_W;
+              const int h = t.h0 - C::PAD + hh, w = t.w0 - C::PAD + ww;
+              if (h >= 0 && h < args.H && w >= 0 && w < args.W) {
+                uint4* p = reinterpret_cast<uint4*>(pl + row * 128 + ((g ^ (row & 7)) << 4));
+                uint4 v = *p;
+                __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h2[e]);
+                  h2[e] = __floats2half2_rn(fmaxf((f.x - mu[2 * e]) * rs[2 * e], 0.f),
+                                            fmaxf((f.y - mu[2 * e + 1]) * rs[2 * e + 1], 0.f));
+                }
+                *p = v;
+              }
+            }
+          }
+          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+          ptx::named_bar_sync(4, 128);
+          if (tt == 0) ptx::mbar_arrive(&planeReady[slot]);
+          if (++slot == C::NSLOT) {
+            slot = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;    // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;  // accumulator row = voxel inside the tile plane
@@ -604,6 +665,22 @@ static int make_convT_out_tmap(CUtensorMap* m, const void* base, int ld, int W2,
   return 0;
 }
 
+template <int KS, int BN, int TD, int MODE, bool STACK, bool XF>
+static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvTcArgs& a, int smem_bytes,
+                      cudaStream_t stream) {
+  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK, XF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
+  const int grid = a.total_tiles < cap ? a.total_tiles : cap;
+  kern<<<grid, XF ? 384 : 256, smem_bytes, stream>>>(tm, tmo, a);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int KS, int BN, int TD, int MODE, bool STACK = false>
 static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
   using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
@@ -618,17 +695,9 @@ static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream)
   a.tiles_h = (a.H + TH - 1) / TH;
   a.tiles_d = (a.D + TD - 1) / TD;
   a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
-  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
-  const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
-  const int grid = a.total_tiles < cap ? a.total_tiles : cap;
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, tmo, a);
-  NC_CUDA(cudaGetLastError());
-  return 0;
+  a.cin_total = Cin;
+  if (a.in_mr) return launch_one<KS, BN, TD, MODE, STACK, true>(tm, tmo, a, C::SMEM_BYTES, stream);
+  return launch_one<KS, BN, TD, MODE, STACK, false>(tm, tmo, a, C::SMEM_BYTES, stream);
 }
 
 int conv3d_k3_bn(int Cout) { return Cout == 64 ? 64 : 128; }
@@ -639,12 +708,13 @@ size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout) {
   return static_cast<size_t>(NB) * ((D + td - 1) / td) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
 }
 
-int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, void* y_raw,
-                  float* stats_partial, cudaStream_t stream) {
+int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin, const void* wpacked,
+                  int Cout, void* y_raw, float* stats_partial, cudaStream_t stream) {
   if (Cin % 64 || Cout % 64) return set_error("conv3d_k3_fwd: Cin and Cout must be multiples of 64");
   ConvTcArgs a{};
   a.W = W, a.H = H, a.D = D, a.NB = NB;
   a.chunks = Cin / 64;
+  a.in_mr = in_mean_rstd;
   a.wpacked = static_cast<const uint8_t*>(wpacked);
   a.out_raw = static_cast<__half*>(y_raw);
   a.stats_partial = stats_partial;
@@ -658,8 +728,9 @@ int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const voi
   return launch_cfg<3, 128, 2, 0>(x, a, Cin, stream);
 }
 
-int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, const float* bias,
-                     int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream) {
+int convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin,
+                     const void* wpacked, const float* bias, int Cout, void* y, int y_ld, int y_coff,
+                     cudaStream_t stream) {
   if (Cin % 64 || (8 * Cout) % 128 || Cout % 32) return set_error("convT3d_k2s2_fwd: unsupported channel counts");
   if (y_ld % 8 || y_coff % 8) return set_error("convT3d_k2s2_fwd: output slice must be 16-byte aligned");
   if (Cout % 64) return set_error("convT3d_k2s2_fwd: Cout must be a multiple of 64");
@@ -667,6 +738,7 @@ int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const 
   ConvTcArgs a{};
   a.W = W, a.H = H, a.D = D, a.NB = NB;
   a.chunks = Cin / 64;
+  a.in_mr = in_mean_rstd;
   a.wpacked = static_cast<const uint8_t*>(wpacked);
   a.out_f16 = static_cast<__half*>(y);
   a.bias = bias;

@@ -31,10 +31,11 @@ void debug_set_max_ctas(int n);
 int conv3d_k3_bn(int Cout);
 int conv3d_k3_td(int Cout);
 size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout);
-int conv3d_k3_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, int Cout, void* y_raw,
-                  float* stats_partial, cudaStream_t stream);
-int convT3d_k2s2_fwd(const void* x, int NB, int D, int H, int W, int Cin, const void* wpacked, const float* bias,
-                     int Cout, void* y, int y_ld, int y_coff, cudaStream_t stream);
+int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin, const void* wpacked,
+                  int Cout, void* y_raw, float* stats_partial, cudaStream_t stream);
+int convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin,
+                     const void* wpacked, const float* bias, int Cout, void* y, int y_ld, int y_coff,
+                     cudaStream_t stream);
 size_t packed_weight_bytes(int Cout, int Cin, int taps, int transposed);
 int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int transposed, cudaStream_t stream);
 

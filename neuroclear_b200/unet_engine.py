@@ -2,20 +2,25 @@
 
 Data layout in HBM (per batch of NB cubes of D x H x W voxels, L0 = full, L1 = /2, L2 = /4 resolution):
 
-    x      fp32 (NB, L0)            dice output / network input
-    raw0   fp16 (NB, L0, 64)        raw conv output of U1, U2, U12 (reused, consumed before rewritten)
-    a1     fp16 (NB, L0, 64)        IN+ReLU(U1)
-    cat1   fp16 (NB, L0, 128)       [IN+ReLU(U2) | t_conv1]          = torch.cat([conv1, t_conv1], 1)
-    p1     fp16 (NB, L1, 64)        maxpool1
-    raw1   fp16 (NB, L1, 128)       raw output of U3, U4, U9, U10
-    a3     fp16 (NB, L1, 128)       IN+ReLU(U3) / (U9) / (U10)
-    cat2   fp16 (NB, L1, 256)       [IN+ReLU(U4) | t_conv2]          = torch.cat([conv2, t_conv2], 1)
-    p2     fp16 (NB, L2, 128)       maxpool2
-    raw2   fp16 (NB, L2, 256)       raw output of U5, U6, U7
-    b1,b2  fp16 (NB, L2, 256)       bottom-layer ping-pong
-    y      fp32 (NB, L0 - 2*crop)   sigmoid output, border already cut
+    x          fp32 (NB, L0)          dice output / network input
+    raw0a/b    fp16 (NB, L0, 64)      raw conv outputs of U1, U2, U12 (ping-pong)
+    a1         fp16 (NB, L0, 64)      IN+ReLU(U1)
+    cat1       fp16 (NB, L0, 128)     [IN+ReLU(U2) | t_conv1]          = torch.cat([conv1, t_conv1], 1)
+    p1         fp16 (NB, L1, 64)      maxpool1
+    raw1a/b    fp16 (NB, L1, 128)     raw outputs of U3, U4, U9, U10
+    cat2       fp16 (NB, L1, 256)     [IN+ReLU(U4) | t_conv2]          = torch.cat([conv2, t_conv2], 1)
+    p2         fp16 (NB, L2, 128)     maxpool2
+    raw2a/b    fp16 (NB, L2, 256)     raw outputs of U5, U6, U7
+    mrA/mrB    fp32 (NB, 2, 256)      (mean, rstd) of the two most recent raw tensors
+    y          fp32 (NB, L0 - 2*crop) sigmoid output, border already cut
 
-All activations are NDHWC; the concat buffers make torch.cat a no-op (producers write channel slices).
+All activations are NDHWC.  Where it pays, InstanceNorm + ReLU between two convolutions is applied INSIDE the
+consumer conv (in_mean_rstd argument of nc_conv3d_k3_fwd): U3->U4, U5->U6->U7, U9->U10 (measured: +4 % on the
+consumer, minus a whole read-raw/write-normalised pass).  A separate apply pass remains (a) for the two skip
+connections, whose pass also produces the max-pooled tensor, (b) in front of U2 (the kd-stacked Cout-64 kernel
+loses 26 % with the in-kernel transform — more than the pass costs) and (c) in front of the transposed convs
+(they re-read their input once per n-tile, so the transform would be repeated 4-8 times).
+The concat buffers make torch.cat a no-op (producers write channel slices).
 Conv biases in front of InstanceNorm(affine=False) cancel exactly in the mean subtraction and are not applied.
 """
 from __future__ import annotations
@@ -103,10 +108,10 @@ class UnetDeconvEngine:
             lib.nc_conv3d_k3_stats_rows(128, nb, d // 4, h // 4, w // 4, 256) * 256,
         )
         ws = dict(
-            raw0=e(nb * l0 * 64, bf), a1=e(nb * l0 * 64, bf), cat1=e(nb * l0 * 128, bf), p1=e(nb * l1 * 64, bf),
-            raw1=e(nb * l1 * 128, bf), a3=e(nb * l1 * 128, bf), cat2=e(nb * l1 * 256, bf), p2=e(nb * l2 * 128, bf),
-            raw2=e(nb * l2 * 256, bf), b1=e(nb * l2 * 256, bf), b2=e(nb * l2 * 256, bf),
-            stats=e(rows * 2, f32), mr=e(nb * 2 * 256, f32),
+            raw0a=e(nb * l0 * 64, bf), raw0b=e(nb * l0 * 64, bf), a1=e(nb * l0 * 64, bf), cat1=e(nb * l0 * 128, bf), p1=e(nb * l1 * 64, bf),
+            raw1a=e(nb * l1 * 128, bf), raw1b=e(nb * l1 * 128, bf), cat2=e(nb * l1 * 256, bf), p2=e(nb * l2 * 128, bf),
+            raw2a=e(nb * l2 * 256, bf), raw2b=e(nb * l2 * 256, bf),
+            stats=e(rows * 2, f32), mrA=e(nb * 2 * 256, f32), mrB=e(nb * 2 * 256, f32),
             fin=torch.zeros(lib.nc_in_stats_scratch_bytes(nb, 256), dtype=torch.uint8, device=dev),
         )
         self._ws_key, self._ws = key, ws
@@ -132,59 +137,56 @@ class UnetDeconvEngine:
         s = stream_ptr()
         lib = _lib.load()
         d1, h1, w1, d2, h2, w2 = d // 2, h // 2, w // 2, d // 4, h // 4, w // 4
-        st, mr = ws["stats"], ws["mr"]
+        st, mrA, mrB = ws["stats"], ws["mrA"], ws["mrB"]
 
-        def stats(cin, dd, hh, ww, c):
+        def stats(cin, dd, hh, ww, c, mr):
             rows = lib.nc_conv3d_k3_stats_rows(cin, nb, dd, hh, ww, c)
             call("nc_in_stats_finalize", ptr(st), nb, i64(rows // nb), c, i64(dd * hh * ww), IN_EPS, ptr(ws["fin"]),
                  ptr(mr), s)
 
-        def conv(prefix, src, dd, hh, ww, cin, cout, raw):
+        def conv(prefix, src, src_mr, dd, hh, ww, cin, cout, raw, raw_mr):
+            """src_mr = (mean, rstd) of `src` when src is a RAW conv output (IN+ReLU fused into this conv), else None"""
             if self.profile is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            call("nc_conv3d_k3_fwd", ptr(src), nb, dd, hh, ww, cin, ptr(self.packed[prefix]), cout, ptr(raw), ptr(st), s)
+            call("nc_conv3d_k3_fwd", ptr(src), ptr(src_mr), nb, dd, hh, ww, cin, ptr(self.packed[prefix]), cout,
+                 ptr(raw), ptr(st), s)
             if self.profile is not None:
                 e1.record()
                 self.profile.append((prefix, 2.0 * nb * dd * hh * ww * cout * cin * 27, e0, e1))
-            stats(cin, dd, hh, ww, cout)
+            stats(cin, dd, hh, ww, cout, raw_mr)
 
-        def apply(raw, dd, hh, ww, c, dst, ld, coff, pooled=None):
+        def apply(raw, mr, dd, hh, ww, c, dst, ld, coff, pooled=None):
             call("nc_in_relu_apply", ptr(raw), ptr(mr), nb, dd, hh, ww, c, ptr(dst), ld, coff, ptr(pooled), s)
 
-        # ---- level 0 down
-        call("nc_conv3d_cin1_k3_fwd", ptr(x), ptr(self.w_first), nb, d, h, w, 64, ptr(ws["raw0"]), ptr(st), s)
-        stats(1, d, h, w, 64)
-        apply(ws["raw0"], d, h, w, 64, ws["a1"], 64, 0)
-        conv("double_conv1.convolution.3", ws["a1"], d, h, w, 64, 64, ws["raw0"])
-        apply(ws["raw0"], d, h, w, 64, ws["cat1"], 128, 0, ws["p1"])                      # conv1 | maxpool1
-        # ---- level 1 down
-        conv("double_conv2.convolution.0", ws["p1"], d1, h1, w1, 64, 128, ws["raw1"])
-        apply(ws["raw1"], d1, h1, w1, 128, ws["a3"], 128, 0)
-        conv("double_conv2.convolution.3", ws["a3"], d1, h1, w1, 128, 128, ws["raw1"])
-        apply(ws["raw1"], d1, h1, w1, 128, ws["cat2"], 256, 0, ws["p2"])                  # conv2 | maxpool2
-        # ---- bottom
-        conv("bottom_layer.convolution.0", ws["p2"], d2, h2, w2, 128, 256, ws["raw2"])
-        apply(ws["raw2"], d2, h2, w2, 256, ws["b1"], 256, 0)
-        conv("bottom_layer.convolution.3", ws["b1"], d2, h2, w2, 256, 256, ws["raw2"])
-        apply(ws["raw2"], d2, h2, w2, 256, ws["b2"], 256, 0)
-        conv("bottom_layer.convolution.6", ws["b2"], d2, h2, w2, 256, 256, ws["raw2"])
-        apply(ws["raw2"], d2, h2, w2, 256, ws["b1"], 256, 0)
-        # ---- level 1 up: cat2 = [conv2 | t_conv2]
-        call("nc_convT3d_k2s2_fwd", ptr(ws["b1"]), nb, d2, h2, w2, 256, ptr(self.packed["t_conv2"]),
+        # ---- level 0 down: U1, U2; conv1 -> cat1[:, :64] and maxpool1
+        call("nc_conv3d_cin1_k3_fwd", ptr(x), ptr(self.w_first), nb, d, h, w, 64, ptr(ws["raw0a"]), ptr(st), s)
+        stats(1, d, h, w, 64, mrA)
+        apply(ws["raw0a"], mrA, d, h, w, 64, ws["a1"], 64, 0)
+        conv("double_conv1.convolution.3", ws["a1"], None, d, h, w, 64, 64, ws["raw0b"], mrB)
+        apply(ws["raw0b"], mrB, d, h, w, 64, ws["cat1"], 128, 0, ws["p1"])
+        # ---- level 1 down: U3, U4; conv2 -> cat2[:, :128] and maxpool2
+        conv("double_conv2.convolution.0", ws["p1"], None, d1, h1, w1, 64, 128, ws["raw1a"], mrA)
+        conv("double_conv2.convolution.3", ws["raw1a"], mrA, d1, h1, w1, 128, 128, ws["raw1b"], mrB)
+        apply(ws["raw1b"], mrB, d1, h1, w1, 128, ws["cat2"], 256, 0, ws["p2"])
+        # ---- bottom: U5, U6, U7
+        conv("bottom_layer.convolution.0", ws["p2"], None, d2, h2, w2, 128, 256, ws["raw2a"], mrA)
+        conv("bottom_layer.convolution.3", ws["raw2a"], mrA, d2, h2, w2, 256, 256, ws["raw2b"], mrB)
+        conv("bottom_layer.convolution.6", ws["raw2b"], mrB, d2, h2, w2, 256, 256, ws["raw2a"], mrA)
+        # ---- level 1 up: cat2 = [conv2 | t_conv2(IN+ReLU(U7))], U9, U10
+        apply(ws["raw2a"], mrA, d2, h2, w2, 256, ws["raw2b"], 256, 0)          # raw2b is free: reuse as IN+ReLU(U7)
+        call("nc_convT3d_k2s2_fwd", ptr(ws["raw2b"]), None, nb, d2, h2, w2, 256, ptr(self.packed["t_conv2"]),
              ptr(self.bias["t_conv2"]), 128, ptr(ws["cat2"]), 256, 128, s)
-        conv("ex_double_conv2.convolution.0", ws["cat2"], d1, h1, w1, 256, 128, ws["raw1"])
-        apply(ws["raw1"], d1, h1, w1, 128, ws["a3"], 128, 0)
-        conv("ex_double_conv2.convolution.3", ws["a3"], d1, h1, w1, 128, 128, ws["raw1"])
-        apply(ws["raw1"], d1, h1, w1, 128, ws["a3"], 128, 0)
-        # ---- level 0 up: cat1 = [conv1 | t_conv1]
-        call("nc_convT3d_k2s2_fwd", ptr(ws["a3"]), nb, d1, h1, w1, 128, ptr(self.packed["t_conv1"]),
+        conv("ex_double_conv2.convolution.0", ws["cat2"], None, d1, h1, w1, 256, 128, ws["raw1a"], mrA)
+        conv("ex_double_conv2.convolution.3", ws["raw1a"], mrA, d1, h1, w1, 128, 128, ws["raw1b"], mrB)
+        # ---- level 0 up: cat1 = [conv1 | t_conv1(IN+ReLU(U10))], U12
+        apply(ws["raw1b"], mrB, d1, h1, w1, 128, ws["raw1a"], 128, 0)          # raw1a is free: reuse as IN+ReLU(U10)
+        call("nc_convT3d_k2s2_fwd", ptr(ws["raw1a"]), None, nb, d1, h1, w1, 128, ptr(self.packed["t_conv1"]),
              ptr(self.bias["t_conv1"]), 64, ptr(ws["cat1"]), 128, 64, s)
-        conv("ex_conv1_1.convolution.0", ws["cat1"], d, h, w, 128, 64, ws["raw0"])
+        conv("ex_conv1_1.convolution.0", ws["cat1"], None, d, h, w, 128, 64, ws["raw0a"], mrA)
         # ---- head: IN + ReLU + 1x1x1 + 1x1x1 + sigmoid (+ border cut)
-        call("nc_head_1x1_sigmoid_fwd", ptr(ws["raw0"]), ptr(mr), ptr(self.head), nb, d, h, w, 64, crop, ptr(out), s)
+        call("nc_head_1x1_sigmoid_fwd", ptr(ws["raw0a"]), ptr(mrA), ptr(self.head), nb, d, h, w, 64, crop, ptr(out), s)
         return out
 
-    #: kernels launched by one forward() (for bench.py's gpu_launches): 1 + 9 convs, 2 convT, 10 finalize,
-    #: 9 apply, 1 head
-    LAUNCHES_PER_FORWARD = 1 + 9 + 2 + 10 + 9 + 1
+    #: kernels launched by one forward(): 1 + 9 convs, 2 convT, 10 finalize, 5 apply(+pool), 1 head
+    LAUNCHES_PER_FORWARD = 1 + 9 + 2 + 10 + 5 + 1

@@ -85,7 +85,7 @@ static int run_check(const Case& c, int mode) {
     CK(cudaMalloc(&dy, vox * c.Cout * 2));
     CK(cudaMemset(dy, 0xFF, vox * c.Cout * 2));
     CK(cudaMalloc(&dst, rows * 2 * c.Cout * 4));
-    NCK(nc_conv3d_k3_fwd(dx, c.NB, c.D, c.H, c.W, c.Cin, dp, c.Cout, dy, dst, nullptr));
+    NCK(nc_conv3d_k3_fwd(dx, nullptr, c.NB, c.D, c.H, c.W, c.Cin, dp, c.Cout, dy, dst, nullptr));
     CK(cudaDeviceSynchronize());
     std::vector<float> y(vox * c.Cout), st(rows * 2 * c.Cout);
     {
@@ -154,7 +154,7 @@ static int run_check(const Case& c, int mode) {
     void* dy;
     CK(cudaMalloc(&dy, ovox * ld * 2));
     CK(cudaMemset(dy, 0, ovox * ld * 2));
-    NCK(nc_convT3d_k2s2_fwd(dx, c.NB, c.D, c.H, c.W, c.Cin, dp, dbias, c.Cout, dy, ld, coff, nullptr));
+    NCK(nc_convT3d_k2s2_fwd(dx, nullptr, c.NB, c.D, c.H, c.W, c.Cin, dp, dbias, c.Cout, dy, ld, coff, nullptr));
     CK(cudaDeviceSynchronize());
     std::vector<__half> y(ovox * ld);
     CK(cudaMemcpy(y.data(), dy, y.size() * 2, cudaMemcpyDeviceToHost));
@@ -213,9 +213,9 @@ static void run_time(const Shape& s, int NB, int iters) {
     float* dst;
     CK(cudaMalloc(&dy, vox * s.Cout * 2));
     CK(cudaMalloc(&dst, rows * 2 * s.Cout * 4));
-    for (int i = 0; i < 2; ++i) NCK(nc_conv3d_k3_fwd(dx, NB, s.D, s.D, s.D, s.Cin, dp, s.Cout, dy, dst, nullptr));
+    for (int i = 0; i < 2; ++i) NCK(nc_conv3d_k3_fwd(dx, nullptr, NB, s.D, s.D, s.D, s.Cin, dp, s.Cout, dy, dst, nullptr));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) NCK(nc_conv3d_k3_fwd(dx, NB, s.D, s.D, s.D, s.Cin, dp, s.Cout, dy, dst, nullptr));
+    for (int i = 0; i < iters; ++i) NCK(nc_conv3d_k3_fwd(dx, nullptr, NB, s.D, s.D, s.D, s.Cin, dp, s.Cout, dy, dst, nullptr));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     flop = 2.0 * vox * s.Cout * s.Cin * 27;
@@ -227,10 +227,10 @@ static void run_time(const Shape& s, int NB, int iters) {
     CK(cudaMalloc(&db, s.Cout * 4));
     CK(cudaMemset(db, 0, s.Cout * 4));
     for (int i = 0; i < 2; ++i)
-      NCK(nc_convT3d_k2s2_fwd(dx, NB, s.D, s.D, s.D, s.Cin, dp, db, s.Cout, dy, 2 * s.Cout, s.Cout, nullptr));
+      NCK(nc_convT3d_k2s2_fwd(dx, nullptr, NB, s.D, s.D, s.D, s.Cin, dp, db, s.Cout, dy, 2 * s.Cout, s.Cout, nullptr));
     CK(cudaEventRecord(e0));
     for (int i = 0; i < iters; ++i)
-      NCK(nc_convT3d_k2s2_fwd(dx, NB, s.D, s.D, s.D, s.Cin, dp, db, s.Cout, dy, 2 * s.Cout, s.Cout, nullptr));
+      NCK(nc_convT3d_k2s2_fwd(dx, nullptr, NB, s.D, s.D, s.D, s.Cin, dp, db, s.Cout, dy, 2 * s.Cout, s.Cout, nullptr));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     flop = 2.0 * vox * s.Cout * s.Cin * 8;

@@ -165,7 +165,7 @@ def test_conv3d_k3_tensor_core(cuda, lib, cin, cout, nb, d, h, w):
     rows = lib.nc_conv3d_k3_stats_rows(cin, nb, d, h, w, cout)
     y = torch.full((nb, d, h, w, cout), float("nan"), dtype=torch.float16, device=cuda)
     st = torch.empty(rows * 2 * cout, device=cuda)
-    call("nc_conv3d_k3_fwd", ptr(xd), nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
+    call("nc_conv3d_k3_fwd", ptr(xd), None, nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
     got = y.cpu().float()
     assert torch.isfinite(got).all()
     assert (got - _ndhwc(ref)).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item())   # fp16 storage
@@ -186,7 +186,7 @@ def test_conv_transpose_into_concat_slice(cuda, lib, cin, cout, d, h, w):
     wd, xd, bd = wt.to(cuda).contiguous(), _ndhwc(x).to(cuda), b.to(cuda)        # keep alive across the launches
     call("nc_pack_weights_convT3d_k2s2", ptr(wd), cin, cout, ptr(packed), stream_ptr())
     cat = torch.full((1, 2 * d, 2 * h, 2 * w, 2 * cout), 7.0, dtype=torch.float16, device=cuda)
-    call("nc_convT3d_k2s2_fwd", ptr(xd), 1, d, h, w, cin, ptr(packed), ptr(bd), cout, ptr(cat), 2 * cout, cout,
+    call("nc_convT3d_k2s2_fwd", ptr(xd), None, 1, d, h, w, cin, ptr(packed), ptr(bd), cout, ptr(cat), 2 * cout, cout,
          stream_ptr())
     got = cat.cpu().float()
     assert (got[..., :cout] == 7.0).all()                                     # the skip half is untouched
@@ -276,3 +276,61 @@ def test_stats_finalize_shared_scratch_across_channel_counts(cuda, lib):
             var = (s2 / n - mean * mean).clamp_min(0)
             got = mr.cpu().double()
             assert torch.allclose(got[:, 0], mean, rtol=1e-6) and torch.allclose(got[:, 1], 1 / torch.sqrt(var + 1e-5), rtol=1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,nb,d,h,w", [(64, 64, 2, 9, 20, 12), (128, 128, 1, 5, 17, 9), (256, 256, 1, 4, 12, 12)])
+def test_conv3d_k3_fused_instance_norm_input(cuda, lib, cin, cout, nb, d, h, w):
+    """in_mean_rstd != NULL: the kernel normalises + ReLUs the RAW input planes in shared memory.  Must equal the
+    two-pass path (nc_in_relu_apply, then conv) BIT FOR BIT: same fp32 expression, same fp16 rounding."""
+    from neuroclear_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(cin * 3 + cout)
+    raw = (torch.randn((nb, d, h, w, cin), generator=g) * 2 + 0.5).half().to(cuda)
+    mean = raw.float().mean(dim=(1, 2, 3))
+    rstd = 1 / torch.sqrt(raw.float().var(dim=(1, 2, 3), unbiased=False) + 1e-5)
+    mr = torch.stack([mean, rstd], 1).contiguous()
+    wt = (torch.randn((cout, cin, 3, 3, 3), generator=g) * (2.0 / (27 * cin)) ** 0.5).to(cuda)
+    packed = torch.empty(lib.nc_packed_weight_bytes(cout, cin, 0), dtype=torch.uint8, device=cuda)
+    call("nc_pack_weights_conv3d_k3", ptr(wt), cout, cin, ptr(packed), stream_ptr())
+    rows = lib.nc_conv3d_k3_stats_rows(cin, nb, d, h, w, cout)
+    outs = []
+    for fused in (False, True):
+        y = torch.full((nb, d, h, w, cout), float("nan"), dtype=torch.float16, device=cuda)
+        st = torch.zeros(rows * 2 * cout, device=cuda)
+        if fused:
+            call("nc_conv3d_k3_fwd", ptr(raw), ptr(mr), nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
+        else:
+            act = torch.empty_like(raw)
+            call("nc_in_relu_apply", ptr(raw), ptr(mr), nb, d, h, w, cin, ptr(act), cin, 0, None, stream_ptr())
+            call("nc_conv3d_k3_fwd", ptr(act), None, nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
+        torch.cuda.synchronize()
+        outs.append((y.clone(), st.clone()))
+    assert torch.isfinite(outs[1][0].float()).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_conv_transpose_fused_instance_norm_input(cuda, lib):
+    from neuroclear_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(21)
+    cin, cout, d, h, w = 128, 64, 4, 18, 10
+    raw = (torch.randn((1, d, h, w, cin), generator=g) * 2 - 0.3).half().to(cuda)
+    mean = raw.float().mean(dim=(1, 2, 3))
+    rstd = 1 / torch.sqrt(raw.float().var(dim=(1, 2, 3), unbiased=False) + 1e-5)
+    mr = torch.stack([mean, rstd], 1).contiguous()
+    wt = (torch.randn((cin, cout, 2, 2, 2), generator=g) * (1.0 / cin) ** 0.5).to(cuda)
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    packed = torch.empty(lib.nc_packed_weight_bytes(cout, cin, 1), dtype=torch.uint8, device=cuda)
+    call("nc_pack_weights_convT3d_k2s2", ptr(wt), cin, cout, ptr(packed), stream_ptr())
+    outs = []
+    for fused in (False, True):
+        cat = torch.zeros((1, 2 * d, 2 * h, 2 * w, 2 * cout), dtype=torch.float16, device=cuda)
+        if fused:
+            call("nc_convT3d_k2s2_fwd", ptr(raw), ptr(mr), 1, d, h, w, cin, ptr(packed), ptr(b), cout, ptr(cat), 2 * cout,
+                 cout, stream_ptr())
+        else:
+            act = torch.empty_like(raw)
+            call("nc_in_relu_apply", ptr(raw), ptr(mr), 1, d, h, w, cin, ptr(act), cin, 0, None, stream_ptr())
+            call("nc_convT3d_k2s2_fwd", ptr(act), None, 1, d, h, w, cin, ptr(packed), ptr(b), cout, ptr(cat), 2 * cout,
+                 cout, stream_ptr())
+        torch.cuda.synchronize()
+        outs.append(cat.clone())
+    assert torch.equal(outs[0], outs[1])
