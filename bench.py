@@ -187,8 +187,8 @@ def main():
     import torch.distributed as dist
     from neuroclear_b200 import _lib
     from neuroclear_b200.pipeline import DicedInference
+    from neuroclear_b200 import networks
     from neuroclear_b200.unet_engine import FLOP_PER_VOXEL
-    from oracle import unet as ounet   # weights only: the seeded random-init state_dict shared with the oracle
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,7 +205,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sd = ounet.random_state_dict(seed=0)
+    # random-init weights of the named architecture through the package's own define_G (kaiming, seed 0); the oracle
+    # is NOT on this arm: it is only executed by cpu_baseline_sample() / --impl reference
+    torch.manual_seed(0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
+    sd = net.state_dict()
     pipe = DicedInference(sd, dev, ROI, OVERLAP, BORDER, normalize_intensity=True, batch=args.batch)
     plan = pipe.plan(shape)
     geo = plan["geo"]

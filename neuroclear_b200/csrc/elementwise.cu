@@ -191,7 +191,7 @@ in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ m
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
                           int C, __half* __restrict__ y, int y_ld, int y_coff,
                           __half* __restrict__ pooled) {
@@ -274,38 +274,45 @@ head_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd,
   const float b1 = __ldg(hp + C), w2 = __ldg(hp + C + 1), b2 = __ldg(hp + C + 2);
   const unsigned voxels = static_cast<unsigned>(D) * H * W;  // per cube: < 2^29 (checked by the launcher)
   const int OD = D - 2 * crop, OH = H - 2 * crop, OW = W - 2 * crop;
-  // a warp handles 4 consecutive voxels per step and two steps per iteration (two 16-byte loads in flight per
-  // lane); the loop bounds are warp-uniform so the shuffles are safe
+  // A warp handles 4 consecutive voxels per step (8 lanes x 8 channels each) and 8 steps per iteration.  The eight
+  // partial dot products of a lane (one per step) are reduced across the 8 lanes of its group by recursive halving
+  // (7 shuffles), which leaves lane `sub` with the complete sum of step `sub`: every lane then finishes ONE voxel
+  // (bias, second 1x1, sigmoid, border test, store) instead of one lane in eight doing all of it.
   const unsigned warps_total = gridDim.x * 8u;
-  for (unsigned q = blockIdx.x * 8u + (threadIdx.x >> 5); q * 4 < voxels; q += 2 * warps_total) {
-    unsigned vox[2];
-    bool ok[2];
-    float o[2][8];
+  const unsigned grp = (threadIdx.x & 31) >> 3;
+  for (unsigned q = blockIdx.x * 8u + (threadIdx.x >> 5); q * 4 < voxels; q += 8 * warps_total) {
+    float part[8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      vox[u] = (q + u * warps_total) * 4 + ((threadIdx.x & 31) >> 3);
-      ok[u] = vox[u] < voxels;
-      const size_t gv = static_cast<size_t>(nb) * voxels + (ok[u] ? vox[u] : 0u);
-      norm8(raw + gv * C + sub * 8, mu, rs, o[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 8; ++u) {
+      const unsigned vox = (q + u * warps_total) * 4 + grp;
+      const size_t gv = static_cast<size_t>(nb) * voxels + (vox < voxels ? vox : 0u);
+      float o[8];
+      norm8(raw + gv * C + sub * 8, mu, rs, o);
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t = fmaf(o[u][i], w1[i], t);
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      t += __shfl_xor_sync(0xffffffffu, t, 4);
-      if (sub == 0 && ok[u]) {
-        const int w = static_cast<int>(vox[u] % W);
-        const unsigned r = vox[u] / W;
-        const int h = static_cast<int>(r % H);
-        const int d = static_cast<int>(r / H);
-        const int od = d - crop, oh = h - crop, ow = w - crop;
-        if (od >= 0 && od < OD && oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
-          const float uu = fmaf(w2, t + b1, b2);
-          y[((static_cast<size_t>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-uu));
-        }
+      for (int i = 0; i < 8; ++i) t = fmaf(o[i], w1[i], t);
+      part[u] = t;
+    }
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+      const bool upper = (sub & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float keep = upper ? part[i + off] : part[i];
+        const float send = upper ? part[i] : part[i + off];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const unsigned vox = (q + sub * warps_total) * 4 + grp;  // the voxel this lane finishes
+    if (vox < voxels) {
+      const int w = static_cast<int>(vox % W);
+      const unsigned r = vox / W;
+      const int h = static_cast<int>(r % H);
+      const int d = static_cast<int>(r / H);
+      const int od = d - crop, oh = h - crop, ow = w - crop;
+      if (od >= 0 && od < OD && oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
+        const float uu = fmaf(w2, part[0] + b1, b2);
+        y[((static_cast<size_t>(nb) * OD + od) * OH + oh) * OW + ow] = 1.0f / (1.0f + expf(-uu));
       }
     }
   }
