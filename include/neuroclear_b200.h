@@ -53,6 +53,12 @@ int nc_dice_extract_u16(const uint16_t* vol /*device*/, int32_t vol_z0, int32_t 
                         int32_t border, int64_t cube_begin, int32_t cube_count, float* cubes /*device*/,
                         nc_stream_t stream);
 
+/* same for --data_type uint8 volumes (divide by 255, base_dataset.py:135-136) */
+int nc_dice_extract_u8(const uint8_t* vol /*device*/, int32_t vol_z0, int32_t vol_nz, const int32_t size_zyx[3],
+                       const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                       int32_t border, int64_t cube_begin, int32_t cube_count, float* cubes /*device*/,
+                       nc_stream_t stream);
+
 /* ---- Unet_deconv layers (models/networks.py:478-538) ------------------------------------------------------ */
 
 /* Number of statistics-partial rows a conv writes for a (NB,D,H,W) output with Cout channels; the partial
@@ -148,6 +154,10 @@ int nc_percentile_lerp(const void* sel_state, double t_lo, double t_hi, double* 
  * NULL => no intensity normalisation. */
 int nc_rescale_u16_crop(const float* vol, int32_t vol_z0, const int32_t padded_zyx[3], const int32_t size_zyx[3],
                         const float* norm3, int32_t z_begin, int32_t z_count, uint16_t* out, nc_stream_t stream);
+
+/* --data_type uint8: *255 + astype(uint8) (assemble_dice.py:195-200) */
+int nc_rescale_u8_crop(const float* vol, int32_t vol_z0, const int32_t padded_zyx[3], const int32_t size_zyx[3],
+                       const float* norm3, int32_t z_begin, int32_t z_count, uint8_t* out, nc_stream_t stream);
 
 /* ---- randomised-depth max-intensity projection (models/axial_to_lateral_gan_apollo_model.py:339-351) ------
  * vol: float32 (D,H,W) single-channel cube; projects planes [start, start+depth) along `axis` (0=z,1=y,2=x)

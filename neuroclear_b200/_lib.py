@@ -23,6 +23,7 @@ SIGNATURES = {
     "nc_debug_set_max_ctas": (None, [i32]),
     "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),
     "nc_dice_extract_u16": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),
+    "nc_dice_extract_u8": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),
     "nc_conv3d_k3_stats_rows": (i64, [i32, i32, i32, i32, i32, i32]),
     "nc_pack_weights_conv3d_cin1_k3": (C.c_int, [vp, vp, vp]),
     "nc_conv3d_cin1_k3_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "nc_select_update": (C.c_int, [i32, vp, vp, vp]),
     "nc_percentile_lerp": (C.c_int, [vp, f64, f64, vp, vp, vp]),
     "nc_rescale_u16_crop": (C.c_int, [vp, i32, I3, I3, vp, i32, i32, vp, vp]),
+    "nc_rescale_u8_crop": (C.c_int, [vp, i32, I3, I3, vp, i32, i32, vp, vp]),
     "nc_mip_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "nc_mip_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
 }

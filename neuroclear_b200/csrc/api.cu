@@ -44,6 +44,13 @@ int nc_dice_extract_u16(const uint16_t* vol, int32_t vol_z0, int32_t vol_nz, con
                           cube_count, cubes, S(stream));
 }
 
+int nc_dice_extract_u8(const uint8_t* vol, int32_t vol_z0, int32_t vol_nz, const int32_t size_zyx[3],
+                       const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                       int32_t border, int64_t cube_begin, int32_t cube_count, float* cubes, nc_stream_t stream) {
+  return dice_extract_u8(vol, vol_z0, vol_nz, size_zyx, padded_zyx, steps_zyx, roi, overlap, border, cube_begin,
+                         cube_count, cubes, S(stream));
+}
+
 int64_t nc_conv3d_k3_stats_rows(int32_t cin, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cout) {
   if (cin == 1) return static_cast<int64_t>(conv_cin1_stats_tiles(nb, d, h, w));
   return static_cast<int64_t>(conv3d_k3_stats_tiles(nb, d, h, w, cout));
@@ -118,6 +125,11 @@ int nc_percentile_lerp(const void* st, double t_lo, double t_hi, double* out64, 
 int nc_rescale_u16_crop(const float* vol, int32_t vol_z0, const int32_t padded_zyx[3], const int32_t size_zyx[3],
                         const float* norm3, int32_t z_begin, int32_t z_count, uint16_t* out, nc_stream_t stream) {
   return rescale_u16_crop(vol, vol_z0, padded_zyx, size_zyx, norm3, z_begin, z_count, out, S(stream));
+}
+
+int nc_rescale_u8_crop(const float* vol, int32_t vol_z0, const int32_t padded_zyx[3], const int32_t size_zyx[3],
+                       const float* norm3, int32_t z_begin, int32_t z_count, uint8_t* out, nc_stream_t stream) {
+  return rescale_u8_crop(vol, vol_z0, padded_zyx, size_zyx, norm3, z_begin, z_count, out, S(stream));
 }
 
 int nc_mip_fwd(const float* vol, int32_t d, int32_t h, int32_t w, int32_t axis, int32_t start, int32_t depth,

@@ -16,7 +16,8 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
   return j;
 }
 
-__global__ void dice_extract_kernel(const uint16_t* __restrict__ vol, int vz0, int vnz, int Z, int Y, int X, int Pz,
+template <typename T>
+__global__ void dice_extract_kernel(const T* __restrict__ vol, int vz0, int vnz, int Z, int Y, int X, int Pz,
                                     int Py, int Px, int ny, int nx, int step, int bc, int E, long long cube_begin,
                                     float* __restrict__ out) {
   const int local_cube = blockIdx.y;
@@ -39,13 +40,14 @@ __global__ void dice_extract_kernel(const uint16_t* __restrict__ vol, int vz0, i
       const int zl = z - vz0;
       if (zl >= 0 && zl < vnz) v = static_cast<float>(vol[(static_cast<size_t>(zl) * Y + y) * X + x]);
     }
-    dst[r] = __fdiv_rn(v, 65535.0f);
+    dst[r] = __fdiv_rn(v, sizeof(T) == 2 ? 65535.0f : 255.0f);   // base_dataset.py:134-143
   }
 }
 
-int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
-                     int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
-                     cudaStream_t stream) {
+template <typename T>
+static int dice_extract_t(const T* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
+                          int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
+                          cudaStream_t stream) {
   if (cube_count <= 0) return 0;
   if (cube_count > 65535) return set_error("dice_extract: at most 65535 cubes per call");
   const int E = roi + 2 * border;
@@ -54,11 +56,22 @@ int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, con
   const unsigned E3 = static_cast<unsigned>(E) * E * E;
   dim3 grid((E3 + 255) / 256, cube_count);
   if (grid.x > 4096) grid.x = 4096;
-  dice_extract_kernel<<<grid, 256, 0, stream>>>(vol, vz0, vnz, size[0], size[1], size[2], padded[0], padded[1],
+  dice_extract_kernel<T><<<grid, 256, 0, stream>>>(vol, vz0, vnz, size[0], size[1], size[2], padded[0], padded[1],
                                                 padded[2], steps[1], steps[2], roi - overlap, border, E, cube_begin,
                                                 cubes);
   NC_CUDA(cudaGetLastError());
   return 0;
+}
+
+int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
+                     int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
+                     cudaStream_t stream) {
+  return dice_extract_t(vol, vz0, vnz, size, padded, steps, roi, overlap, border, cube_begin, cube_count, cubes, stream);
+}
+int dice_extract_u8(const uint8_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
+                    int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
+                    cudaStream_t stream) {
+  return dice_extract_t(vol, vz0, vnz, size, padded, steps, roi, overlap, border, cube_begin, cube_count, cubes, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
@@ -528,9 +541,10 @@ int percentile_lerp(const void* st, double t_lo, double t_hi, double* out64, flo
 }
 
 // ------------------------------------------------------------------------------------------------ rescale
+template <typename T>
 __global__ void __launch_bounds__(256)
-rescale_u16_crop_kernel(const float* __restrict__ vol, int vol_z0, int Py, int Px, int Y, int X,
-                        const float* __restrict__ norm3, int z_begin, uint16_t* __restrict__ out) {
+rescale_crop_kernel(const float* __restrict__ vol, int vol_z0, int Py, int Px, int Y, int X,
+                    const float* __restrict__ norm3, int z_begin, T* __restrict__ out) {
   const int x = blockIdx.x * 256 + threadIdx.x;
   if (x >= X) return;
   const int y = blockIdx.y;
@@ -545,20 +559,29 @@ rescale_u16_crop_kernel(const float* __restrict__ vol, int vol_z0, int Py, int P
       v = fminf(fmaxf(v, 0.f), 1.f);
     }
   }
-  v = __fmul_rn(v, 65535.0f);                   // *= 2**16 - 1
-  out[(static_cast<size_t>(blockIdx.z) * Y + y) * X + x] = static_cast<uint16_t>(static_cast<int>(v));  // truncation
+  v = __fmul_rn(v, sizeof(T) == 2 ? 65535.0f : 255.0f);   // *= 2**16 - 1 (or 255)
+  out[(static_cast<size_t>(blockIdx.z) * Y + y) * X + x] = static_cast<T>(static_cast<int>(v));  // truncation
 }
 
-int rescale_u16_crop(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3,
-                     int z_begin, int z_count, uint16_t* out, cudaStream_t stream) {
+template <typename T>
+static int rescale_crop_t(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3,
+                          int z_begin, int z_count, T* out, cudaStream_t stream) {
   if (z_count <= 0) return 0;
   if (z_count > 65535 || size[1] > 65535) return set_error("rescale_u16_crop: slab too large for one launch");
   if (z_begin < vol_z0 || z_begin + z_count > size[0]) return set_error("rescale_u16_crop: plane range out of bounds");
   dim3 grid((size[2] + 255) / 256, size[1], z_count);
-  rescale_u16_crop_kernel<<<grid, 256, 0, stream>>>(vol, vol_z0, padded[1], padded[2], size[1], size[2], norm3,
-                                                    z_begin, out);
+  rescale_crop_kernel<T><<<grid, 256, 0, stream>>>(vol, vol_z0, padded[1], padded[2], size[1], size[2], norm3, z_begin,
+                                                   out);
   NC_CUDA(cudaGetLastError());
   return 0;
+}
+int rescale_u16_crop(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3,
+                     int z_begin, int z_count, uint16_t* out, cudaStream_t stream) {
+  return rescale_crop_t(vol, vol_z0, padded, size, norm3, z_begin, z_count, out, stream);
+}
+int rescale_u8_crop(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3, int z_begin,
+                    int z_count, uint8_t* out, cudaStream_t stream) {
+  return rescale_crop_t(vol, vol_z0, padded, size, norm3, z_begin, z_count, out, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ MIP

@@ -44,6 +44,11 @@ int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int tra
 int dice_extract_u16(const uint16_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
                      int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
                      cudaStream_t stream);
+int dice_extract_u8(const uint8_t* vol, int vz0, int vnz, const int* size, const int* padded, const int* steps,
+                    int roi, int overlap, int border, long long cube_begin, int cube_count, float* cubes,
+                    cudaStream_t stream);
+int rescale_u8_crop(const float* vol, int vol_z0, const int* padded, const int* size, const float* norm3, int z_begin,
+                    int z_count, uint8_t* out, cudaStream_t stream);
 size_t conv_cin1_stats_tiles(int NB, int D, int H, int W);
 // conv1_tc.cu
 int pack_conv1_weights(const float* w, void* packed, cudaStream_t stream);

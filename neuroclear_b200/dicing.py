@@ -56,16 +56,17 @@ def dice_geometry(size, roi: int, overlap: int, border: int = 0) -> DiceGeometry
 # ---------------------------------------------------------------------------------------------- device ops
 def dice_extract(vol_dev: torch.Tensor, vol_z0: int, geo: DiceGeometry, cube_begin: int, count: int,
                  out: torch.Tensor = None) -> torch.Tensor:
-    """vol_dev: uint16 CUDA planes [vol_z0, vol_z0+n) of the original volume -> float32 (count, E, E, E)."""
+    """vol_dev: uint16 / uint8 CUDA planes [vol_z0, vol_z0+n) of the original volume -> float32 (count, E, E, E)."""
     if not vol_dev.is_cuda:
         raise NeuroclearError("dice_extract: the volume must be in device memory (no CPU fallback)")
-    assert vol_dev.dtype == torch.uint16 and vol_dev.is_contiguous()
+    assert vol_dev.dtype in (torch.uint16, torch.uint8) and vol_dev.is_contiguous()
     e = geo.edge
     if out is None:
         out = torch.empty((count, e, e, e), dtype=torch.float32, device=vol_dev.device)
     size, padded, steps = geo.c_arrays()
-    call("nc_dice_extract_u16", ptr(vol_dev), vol_z0, vol_dev.shape[0], size, padded, steps, geo.roi, geo.overlap,
-         geo.border, i64(cube_begin), count, ptr(out), stream_ptr())
+    fn = "nc_dice_extract_u16" if vol_dev.dtype == torch.uint16 else "nc_dice_extract_u8"
+    call(fn, ptr(vol_dev), vol_z0, vol_dev.shape[0], size, padded, steps, geo.roi, geo.overlap, geo.border,
+         i64(cube_begin), count, ptr(out), stream_ptr())
     return out
 
 
@@ -112,11 +113,14 @@ class PercentileSelect:
         return self.norm3, self.out64
 
 
-def rescale_u16_crop(vis: torch.Tensor, vis_z0: int, geo: DiceGeometry, norm3, z_begin: int, z_count: int, out=None):
+def rescale_u16_crop(vis: torch.Tensor, vis_z0: int, geo: DiceGeometry, norm3, z_begin: int, z_count: int, out=None,
+                     dtype=torch.uint16):
+    """rescale + cast + un-pad; dtype uint16 (default) or uint8 (--data_type)."""
     if out is None:
-        out = torch.empty((z_count, geo.size[1], geo.size[2]), dtype=torch.uint16, device=vis.device)
+        out = torch.empty((z_count, geo.size[1], geo.size[2]), dtype=dtype, device=vis.device)
     size, padded, _ = geo.c_arrays()
-    call("nc_rescale_u16_crop", ptr(vis), vis_z0, padded, size, ptr(norm3), z_begin, z_count, ptr(out), stream_ptr())
+    fn = "nc_rescale_u16_crop" if out.dtype == torch.uint16 else "nc_rescale_u8_crop"
+    call(fn, ptr(vis), vis_z0, padded, size, ptr(norm3), z_begin, z_count, ptr(out), stream_ptr())
     return out
 
 
@@ -155,8 +159,8 @@ class DiceImageDataSet:
         self.overlap = opt.overlap
         self.border_cut = opt.border_cut
         vol = volume if volume is not None else _load_volume(opt.dataroot)
-        if vol.dtype != np.uint16:
-            raise NeuroclearError("the B200 dice path takes 16-bit volumes (--data_type uint16)")
+        if vol.dtype not in (np.uint16, np.uint8):
+            raise NeuroclearError("the dice path takes uint16 or uint8 volumes (--data_type)")
         if "addColorChannel" not in getattr(opt, "preprocess", "addColorChannel"):
             raise NeuroclearError("DiceImageDataSet expects --preprocess addColorChannel as in the reference README")
         gpu_ids = getattr(opt, "gpu_ids", [0])
@@ -219,8 +223,8 @@ class Assemble_Dice:
         self.z_steps, self.y_steps, self.x_steps = self.geo.steps
         self.visual_names = ["real", "fake"]
         self.imtype = opt.data_type
-        if self.imtype != "uint16":
-            raise NeuroclearError("Assemble_Dice (B200): only --data_type uint16 is implemented")
+        if self.imtype not in ("uint16", "uint8"):
+            raise NeuroclearError("Assemble_Dice (B200): --data_type must be uint16 or uint8")
         self.skip_real = opt.skip_real
         if getattr(opt, "histogram_match", False):
             raise NotImplementedError("--histogram_match is outside the B200 hot path (SURVEY.md §8f-3)")
@@ -295,7 +299,8 @@ class Assemble_Dice:
                 if self.normalize_intensity:
                     norm3, p64 = sel.run(vis, vis.numel(), (self.p1, self.p99))
                     self.percentiles[name] = p64
-                out = rescale_u16_crop(vis, 0, g, norm3, 0, g.size[0])
+                out = rescale_u16_crop(vis, 0, g, norm3, 0, g.size[0],
+                                       dtype=torch.uint16 if self.imtype == "uint16" else torch.uint8)
                 del vis
                 self.visual_ret[name] = out.cpu().numpy()
                 if name in self.percentiles:

@@ -41,6 +41,7 @@ class DicedInference:
             self.select = PercentileSelect(self.device)
         self._plan_key = None
         self.last = {}
+        self.out_dtype = torch.uint16     # follows the input volume's dtype (--data_type uint16 | uint8)
 
     # ---------------------------------------------------------------- static plan for a volume shape
     def plan(self, size):
@@ -73,6 +74,7 @@ class DicedInference:
         return volume_host[z0:z1].to(self.device, non_blocking=True), z0
 
     def infer_cubes(self, vol_dev, vol_z0, plan, queue=None):
+        self.out_dtype = vol_dev.dtype
         geo = plan["geo"]
         c0, c1 = plan["cubes"]
         r, e = self.roi, geo.edge
@@ -100,7 +102,7 @@ class DicedInference:
             norm3, self.last["percentiles"] = self.select.run(vis, n_total, self.sat_level, self.group,
                                                               distributed=self.world > 1)
         o0, o1 = plan["out_planes"]
-        return rescale_u16_crop(vis, s0, geo, norm3, o0, o1 - o0)
+        return rescale_u16_crop(vis, s0, geo, norm3, o0, o1 - o0, dtype=self.out_dtype)
 
     # ---------------------------------------------------------------- public API
     def run_device(self, vol_dev, vol_z0, size):
@@ -121,7 +123,7 @@ class DicedInference:
             vol_dev = slab_host.to(self.device, non_blocking=True)
             out_dev = self.run_device(vol_dev, z0, tuple(size))
             if out_host is None:
-                out_host = torch.empty(out_dev.shape, dtype=torch.uint16, pin_memory=True)
+                out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return out_host.numpy(), plan["out_planes"]
@@ -131,14 +133,14 @@ class DicedInference:
         slab of the assembled uint16 volume as a host numpy array (the whole volume when not sharded)."""
         if isinstance(volume, np.ndarray):
             volume = torch.from_numpy(volume)
-        if volume.dtype != torch.uint16 or volume.dim() != 3:
-            raise NeuroclearError("DicedInference.run expects a (Z,Y,X) uint16 volume")
+        if volume.dtype not in (torch.uint16, torch.uint8) or volume.dim() != 3:
+            raise NeuroclearError("DicedInference.run expects a (Z,Y,X) uint16 or uint8 volume")
         with torch.cuda.device(self.device):
             plan = self.plan(tuple(volume.shape))
             vol_dev, z0 = self.upload(volume, plan)
             out_dev = self.run_device(vol_dev, z0, tuple(volume.shape))
             if out_host is None:
-                out_host = torch.empty(out_dev.shape, dtype=torch.uint16, pin_memory=True)
+                out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return out_host.numpy(), plan["out_planes"]

@@ -201,3 +201,27 @@ def test_assembly_error_behaviour_matches_reference(cuda):
         Assemble_Dice(_opt(24, 0, 4), ds)
     with pytest.raises(NeuroclearError):
         DiceImageDataSet(_opt(24, 6, 4), volume=vol.astype(np.uint8))
+
+
+def test_uint8_data_type(cuda):
+    """--data_type uint8 (base_dataset.py:135-136, assemble_dice.py:195-200): /255 in, *255 + astype(uint8) out."""
+    from neuroclear_b200.dicing import blend_gather, dice_extract, dice_geometry, rescale_u16_crop
+    rng = np.random.default_rng(12)
+    vol = rng.integers(0, 256, (40, 47, 61), dtype=np.uint8)
+    g, og = dice_geometry(vol.shape, 24, 6, 4), ogeo.dice_geometry(vol.shape, 24, 6, 4)
+    dev = torch.from_numpy(vol).to(cuda)
+    cubes = dice_extract(dev, 0, g, 0, g.n_cubes)
+    for i in (0, g.n_cubes // 2, g.n_cubes - 1):
+        assert np.array_equal(cubes[i].cpu().numpy()[None], dice.dice_cube_gather(vol, og, i))
+    fake = rng.random((g.n_cubes, 1, 32, 32, 32), dtype=np.float32)
+    ref, pcts = assemble.assemble(list(fake), og, True)                      # uint16 path for the percentiles ...
+    blend, _ = assemble.blend_sequential([assemble.crop_border(c, 4) for c in fake], og)
+    ref8, _ = assemble.finish(blend, og, True, imtype="uint8")               # ... and the reference's uint8 branch
+    q = torch.from_numpy(np.stack([assemble.crop_border(c, 4) for c in fake])).to(cuda)
+    off = torch.arange(g.n_cubes, dtype=torch.int64, device=cuda) * 24 ** 3
+    zz = torch.zeros(g.n_cubes, dtype=torch.int32, device=cuda)
+    vis = blend_gather(q.view(-1), off, zz, g, 0, g.padded[0])
+    from neuroclear_b200.dicing import PercentileSelect
+    norm3, _ = PercentileSelect(cuda).run(vis, vis.numel(), (0.25, 99.75))
+    out8 = rescale_u16_crop(vis, 0, g, norm3, 0, g.size[0], dtype=torch.uint8).cpu().numpy()
+    assert out8.dtype == np.uint8 and np.array_equal(out8, ref8)

@@ -44,6 +44,12 @@ def test_dice_matches_reference_cubes():
         assert np.array_equal(f["cubes"][i], dice.dice_cube_gather(vol, g, i))
 
 
+def test_u8_normalise_is_fp32_divide():
+    v = np.arange(256, dtype=np.uint8)
+    ref = torch.from_numpy((v / (2 ** 8 * 1.0 - 1)).astype(float)).float().numpy()     # base_dataset.py:135-136
+    assert np.array_equal(ref, v.astype(np.float32) / np.float32(255.0))
+
+
 def test_u16_normalise_is_fp32_divide():
     v = np.arange(65536, dtype=np.uint16)
     ref = torch.from_numpy((v / (2 ** 16 * 1.0 - 1)).astype(float)).float().numpy()   # base_dataset.py:134-143,291-295
