@@ -330,11 +330,9 @@ int conv3d_cin1_k3_fwd(const float* x, const void* wpacked, int NB, int D, int H
   a.NB = NB, a.D = D, a.H = H, a.W = W;
   a.tiles_w = (W + c1::TW - 1) / c1::TW, a.tiles_h = (H + c1::TH - 1) / c1::TH;
   a.tiles_per_cube = D * a.tiles_h * a.tiles_w;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {false};
+  if (first_use_on_device(attr))
     NC_CUDA(cudaFuncSetAttribute(conv_cin1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1::SMEM_BYTES));
-    attr = true;
-  }
   conv_cin1_tc_kernel<<<conv1_grid(a.tiles_per_cube), c1::THREADS, c1::SMEM_BYTES, stream>>>(tm, a);
   NC_CUDA(cudaGetLastError());
   return 0;

@@ -669,11 +669,9 @@ template <int KS, int BN, int TD, int MODE, bool STACK, bool XF>
 static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvTcArgs& a, int smem_bytes,
                       cudaStream_t stream) {
   auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK, XF>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (first_use_on_device(attr_set))
     NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
   const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
   const int grid = a.total_tiles < cap ? a.total_tiles : cap;
   kern<<<grid, XF ? 384 : 256, smem_bytes, stream>>>(tm, tmo, a);

@@ -519,11 +519,9 @@ int select_histogram(const float* data, long long n, int pass, const void* st, u
   if (reinterpret_cast<uintptr_t>(data) & 15) return set_error("select_histogram: data must be 16-byte aligned");
   const int ntab = pass == 0 ? 1 : 4;
   const size_t smem = static_cast<size_t>(ntab) * (1 << sel_bits(pass)) * sizeof(unsigned int);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {false};
+  if (first_use_on_device(attr))
     NC_CUDA(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SEL_BINS * 4));
-    attr = true;
-  }
   select_hist_kernel<<<num_sms() * 2, 512, smem, stream>>>(data, n, pass, static_cast<const SelectState*>(st), hist);
   NC_CUDA(cudaGetLastError());
   return 0;

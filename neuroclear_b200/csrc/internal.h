@@ -18,6 +18,9 @@ int set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property: true the first time `flags` (a static
+// 64-entry array owned by the call site) is asked about the current device.
+bool first_use_on_device(bool* flags);
 
 using TensorMapEncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

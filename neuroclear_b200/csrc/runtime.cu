@@ -30,6 +30,14 @@ int num_sms() {
   return cached[dev];
 }
 
+bool first_use_on_device(bool* flags) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const bool first = !flags[dev];
+  flags[dev] = true;
+  return first;
+}
+
 TensorMapEncodeTiledFn get_tensor_map_encoder() {
   static TensorMapEncodeTiledFn fn = nullptr;
   static bool tried = false;

@@ -334,3 +334,30 @@ def test_conv_transpose_fused_instance_norm_input(cuda, lib):
         torch.cuda.synchronize()
         outs.append(cat.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (128, 64)])
+def test_conv3d_persistent_grid_cap_is_bit_identical(cuda, lib, cin, cout):
+    """nc_debug_set_max_ctas(2) makes every CTA walk many tiles (plane / weight ring wrap-around, TMEM ping-pong):
+    the result must not change by a bit."""
+    from neuroclear_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(cin + 7 * cout)
+    nb, d, h, w = 2, 10, 21, 19
+    x = torch.randn((nb, d, h, w, cin), generator=g).half().to(cuda)
+    wt = (torch.randn((cout, cin, 3, 3, 3), generator=g) * (2.0 / (27 * cin)) ** 0.5).to(cuda)
+    packed = torch.empty(lib.nc_packed_weight_bytes(cout, cin, 0), dtype=torch.uint8, device=cuda)
+    call("nc_pack_weights_conv3d_k3", ptr(wt), cout, cin, ptr(packed), stream_ptr())
+    rows = lib.nc_conv3d_k3_stats_rows(cin, nb, d, h, w, cout)
+    outs = []
+    try:
+        for cap in (0, 2, 5):
+            lib.nc_debug_set_max_ctas(cap)
+            y = torch.zeros((nb, d, h, w, cout), dtype=torch.float16, device=cuda)
+            st = torch.zeros(rows * 2 * cout, device=cuda)
+            call("nc_conv3d_k3_fwd", ptr(x), None, nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
+            torch.cuda.synchronize()
+            outs.append((y, st))
+    finally:
+        lib.nc_debug_set_max_ctas(0)
+    for y, st in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(st, outs[0][1])
