@@ -3,22 +3,25 @@
 // Replaces the torch.nn.Conv3d / ConvTranspose3d calls of Unet_deconv (reference models/networks.py:478-538,
 // layers U2..U12 of SURVEY.md §2c). Design (not a translation of any library kernel):
 //
-//   * activations are fp16 NDHWC (fp16, not bf16: see DESIGN.md "Operand precision"); one GEMM row = one voxel, K = taps x Cin walked as (64-channel chunk, tap)
+//   * activations are fp16 NDHWC (fp16, not bf16: see DESIGN.md "Operand precision"); one GEMM row = one voxel,
+//     K = taps x Cin walked as (64-channel chunk, tap)
 //   * a CTA owns an output tile of 8(w) x 16(h) x TD(d) voxels = TD accumulators of 128 rows in TMEM
 //   * the input is staged ONCE per (tile, chunk) as TD+KS-1 halo planes of (8+KS-1) x (16+KS-1) voxels, each
 //     voxel one 128-byte row, written by a 5-D TMA box with SWIZZLE_128B (out-of-volume rows arrive as zeros
 //     = the conv's zero padding). Every filter tap is then just a shifted window into those planes: the
 //     UMMA shared-memory descriptor's start address moves by (kh*(8+KS-1)+kw) rows and the plane index by kd,
 //     with the 8-row-group stride set to one halo line. Input traffic drops from 27x to ~2x of the tile.
-//   * weights are pre-packed per (n-tile, chunk, tap) as the exact swizzled shared-memory image and streamed
-//     with 1-D bulk copies through a ring; one weight stage feeds TD MMAs (one per output plane).
-//   * warp roles: 0 = halo-plane TMA producer, 1 = MMA issuer, 2 = TMEM allocator + weight producer,
-//     4..7 = epilogue (TMEM -> registers -> global). Two accumulator sets ping-pong so the epilogue of
-//     tile i overlaps the MMAs of tile i+1. The grid is persistent (<= #SMs CTAs, static tile stride).
+//   * weights are pre-packed as the exact swizzled shared-memory image and streamed with 1-D bulk copies through
+//     a ring; one weight stage feeds the MMAs of all TD output planes.
+//   * warp roles: 0 = halo-plane TMA producer, 1 = MMA issuer (warp-uniform loops, one elected lane issues),
+//     2 = TMEM allocator + weight producer, 4..7 = epilogue, 8..11 (XF only) = in-place InstanceNorm + ReLU of the
+//     landed planes. Two accumulator sets ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1.
+//     The grid is persistent (<= #SMs CTAs, static tile stride).
+//   * STACK (Cout = 64): the three kd taps of a (kh,kw) are stacked along N (N = 64/128/192 MMAs), see ConvCfg.
 //   * epilogue MODE 0: raw fp16 NDHWC store + per-tile per-channel (sum, sum of squares) partials taken from
 //     the fp32 accumulators (InstanceNorm statistics, reduced deterministically later);
-//     MODE 1: transposed-conv scatter (voxel (2d+a,2h+b,2w+c)), +bias, fp16 store into a channel slice of the
-//     skip-concat buffer.
+//     MODE 1: transposed conv — + bias, fp16 tile staged in shared memory and written by a TMA store whose tensor
+//     map walks the fine grid with element stride 2 (pixel shuffle) into a channel slice of the concat buffer.
 #include <cuda_fp16.h>
 
 #include "internal.h"

@@ -51,7 +51,7 @@ static const Case cases[] = {
 };
 static const int ncases = sizeof(cases) / sizeof(cases[0]);
 
-static int run_check(const Case& c, int mode) {
+static int run_check(const Case& c, int cap) {
   const size_t vox = (size_t)c.NB * c.D * c.H * c.W;
   std::vector<float> x(vox * c.Cin);
   std::vector<__half> xb(x.size());
@@ -144,7 +144,7 @@ static int run_check(const Case& c, int mode) {
             fabs(q - rsq[(size_t)n * c.Cout + co]) > 3e-3 * (1 + fabs(q)))
           ++sbad;
       }
-    printf("%s mode=%d: %lld/%zu mismatching outputs, max |err| %.4g, stats mismatches %lld -> %s\n", c.name, mode,
+    printf("%s cap=%d: %lld/%zu mismatching outputs, max |err| %.4g, stats mismatches %lld -> %s\n", c.name, cap,
            bad, vox * c.Cout, maxerr, sbad, (bad == 0 && sbad == 0) ? "PASS" : "FAIL");
     return (bad == 0 && sbad == 0) ? 0 : 1;
   } else {
@@ -245,10 +245,10 @@ static void run_time(const Shape& s, int NB, int iters) {
 int main(int argc, char** argv) {
   if (argc >= 3 && !strcmp(argv[1], "check")) {
     const int ci = atoi(argv[2]);
-    const int mode = argc > 3 ? atoi(argv[3]) : 0;   // persistent-grid cap: > 0 forces several tiles per CTA
+    const int cap = argc > 3 ? atoi(argv[3]) : 0;   // persistent-grid cap: > 0 forces several tiles per CTA
     if (ci < 0 || ci >= ncases) return 4;
-    nc_debug_set_max_ctas(mode);
-    return run_check(cases[ci], mode);
+    nc_debug_set_max_ctas(cap);
+    return run_check(cases[ci], cap);
   }
   if (argc >= 3 && !strcmp(argv[1], "time")) {
     const int si = atoi(argv[2]);
