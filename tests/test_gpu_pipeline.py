@@ -200,7 +200,7 @@ def test_assembly_error_behaviour_matches_reference(cuda):
     with pytest.raises(NeuroclearError):
         Assemble_Dice(_opt(24, 0, 4), ds)
     with pytest.raises(NeuroclearError):
-        DiceImageDataSet(_opt(24, 6, 4), volume=vol.astype(np.uint8))
+        DiceImageDataSet(_opt(24, 6, 4), volume=vol.astype(np.float32))   # only uint16 / uint8 volumes
 
 
 def test_uint8_data_type(cuda):

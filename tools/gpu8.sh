@@ -3,7 +3,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 python -m pytest tests/test_gpu_multi.py -q --timeout 900 2>&1 | tail -2
-for n in 8 4; do
+for n in 8 4 2; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
   tail -c 400 gpurun_out/bench_n$n.err | tail -2
   python - <<PY
