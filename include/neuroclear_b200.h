@@ -168,6 +168,33 @@ int nc_mip_fwd(const float* vol, int32_t d, int32_t h, int32_t w, int32_t axis, 
 int nc_mip_bwd(const float* grad_proj, const int32_t* argmax, int32_t d, int32_t h, int32_t w, int32_t axis,
                float* grad_vol /* accumulated into */, nc_stream_t stream);
 
+/* ---- 2-D PatchGAN discriminator path of the apollo model (training) ------------------------------------------
+ * NLayerDiscriminator(dimension=2) (models/networks.py:1009-1067, built at
+ * models/axial_to_lateral_gan_apollo_model.py:99-123): Conv2d(k4, p1, stride 1|2) forward / data gradient / weight
+ * (+bias) gradient, InstanceNorm2d(affine=False)+LeakyReLU forward / backward, LeakyReLU backward, and the two
+ * losses of the step (GANLoss 'lsgan' networks.py:252-319 = MSE against a constant; torch.nn.L1Loss
+ * apollo_model.py:128).  fp32, NCHW, latency-bound by nature (one ~108^2 image per pass).
+ * x (N,Cin,H,W), w (Cout,Cin,4,4) and b (Cout) as in the state_dict, y (N,Cout,Ho,Wo), Ho = (H-2)/stride + 1.
+ * lrelu_slope = 1 -> no activation; 0.2 fuses the LeakyReLU(0.2) that follows the first conv. */
+int nc_conv2d_k4_fwd(const float* x, const float* w, const float* b /*nullable*/, int32_t n, int32_t cin, int32_t h,
+                     int32_t wd, int32_t cout, int32_t stride, float lrelu_slope, float* y, nc_stream_t stream);
+int nc_conv2d_k4_dgrad(const float* dy, const float* w, int32_t n, int32_t cin, int32_t h, int32_t wd, int32_t cout,
+                       int32_t stride, float* dx, nc_stream_t stream);
+int nc_conv2d_k4_wgrad(const float* x, const float* dy, int32_t n, int32_t cin, int32_t h, int32_t wd, int32_t cout,
+                       int32_t stride, float* dw, float* db /*nullable*/, nc_stream_t stream);
+/* x, y, dy, dx: (nc_planes, plane) = (N*C, H*W); mean_rstd: (nc_planes, 2) saved by fwd for bwd; eps = 1e-5 */
+int nc_in2d_lrelu_fwd(const float* x, int32_t nc_planes, int32_t plane, float eps, float slope, float* y,
+                      float* mean_rstd, nc_stream_t stream);
+int nc_in2d_lrelu_bwd(const float* dy, const float* x, const float* mean_rstd, int32_t nc_planes, int32_t plane,
+                      float slope, float* dx, nc_stream_t stream);
+/* dx = dy * (y > 0 ? 1 : slope) with y the OUTPUT of the (fused) LeakyReLU */
+int nc_lrelu_bwd(const float* dy, const float* y, int64_t n, float slope, float* dx, nc_stream_t stream);
+/* mode 0: loss = mean((p - target)^2) (q unused); mode 1: loss = mean(|p - q|).  bwd: dp = *upstream * dloss/dp */
+int nc_loss_fwd(const float* p, const float* q, float target, int64_t n, int32_t mode, float* loss,
+                nc_stream_t stream);
+int nc_loss_bwd(const float* p, const float* q, float target, int64_t n, int32_t mode, const float* upstream,
+                float* dp, nc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,14 @@ SIGNATURES = {
     "nc_rescale_u8_crop": (C.c_int, [vp, i32, I3, I3, vp, i32, i32, vp, vp]),
     "nc_mip_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "nc_mip_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+    "nc_conv2d_k4_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]),
+    "nc_conv2d_k4_dgrad": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "nc_conv2d_k4_wgrad": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "nc_in2d_lrelu_fwd": (C.c_int, [vp, i32, i32, f32, f32, vp, vp, vp]),
+    "nc_in2d_lrelu_bwd": (C.c_int, [vp, vp, vp, i32, i32, f32, vp, vp]),
+    "nc_lrelu_bwd": (C.c_int, [vp, vp, i64, f32, vp, vp]),
+    "nc_loss_fwd": (C.c_int, [vp, vp, f32, i64, i32, vp, vp]),
+    "nc_loss_bwd": (C.c_int, [vp, vp, f32, i64, i32, vp, vp, vp]),
 }
 
 _lib = None

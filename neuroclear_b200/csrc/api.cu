@@ -141,4 +141,36 @@ int nc_mip_bwd(const float* gproj, const int32_t* argmax, int32_t d, int32_t h, 
   return mip_bwd(gproj, argmax, d, h, w, axis, gvol, S(stream));
 }
 
+int nc_conv2d_k4_fwd(const float* x, const float* w, const float* b, int32_t n, int32_t cin, int32_t h, int32_t wd,
+                     int32_t cout, int32_t stride, float lrelu_slope, float* y, nc_stream_t stream) {
+  return conv2d_k4_fwd(x, w, b, n, cin, h, wd, cout, stride, lrelu_slope, y, S(stream));
+}
+int nc_conv2d_k4_dgrad(const float* dy, const float* w, int32_t n, int32_t cin, int32_t h, int32_t wd, int32_t cout,
+                       int32_t stride, float* dx, nc_stream_t stream) {
+  return conv2d_k4_dgrad(dy, w, n, cin, h, wd, cout, stride, dx, S(stream));
+}
+int nc_conv2d_k4_wgrad(const float* x, const float* dy, int32_t n, int32_t cin, int32_t h, int32_t wd, int32_t cout,
+                       int32_t stride, float* dw, float* db, nc_stream_t stream) {
+  return conv2d_k4_wgrad(x, dy, n, cin, h, wd, cout, stride, dw, db, S(stream));
+}
+int nc_in2d_lrelu_fwd(const float* x, int32_t nc_planes, int32_t plane, float eps, float slope, float* y,
+                      float* mean_rstd, nc_stream_t stream) {
+  return in2d_lrelu_fwd(x, nc_planes, plane, eps, slope, y, mean_rstd, S(stream));
+}
+int nc_in2d_lrelu_bwd(const float* dy, const float* x, const float* mean_rstd, int32_t nc_planes, int32_t plane,
+                      float slope, float* dx, nc_stream_t stream) {
+  return in2d_lrelu_bwd(dy, x, mean_rstd, nc_planes, plane, slope, dx, S(stream));
+}
+int nc_lrelu_bwd(const float* dy, const float* y, int64_t n, float slope, float* dx, nc_stream_t stream) {
+  return lrelu_bwd(dy, y, n, slope, dx, S(stream));
+}
+int nc_loss_fwd(const float* p, const float* q, float target, int64_t n, int32_t mode, float* loss,
+                nc_stream_t stream) {
+  return loss_fwd(p, q, target, n, mode, loss, S(stream));
+}
+int nc_loss_bwd(const float* p, const float* q, float target, int64_t n, int32_t mode, const float* upstream,
+                float* dp, nc_stream_t stream) {
+  return loss_bwd(p, q, target, n, mode, upstream, dp, S(stream));
+}
+
 }  // extern "C"

@@ -77,6 +77,22 @@ int mip_fwd(const float* vol, int D, int H, int W, int axis, int start, int dept
             cudaStream_t stream);
 int mip_bwd(const float* gproj, const int* argmax, int D, int H, int W, int axis, float* gvol, cudaStream_t stream);
 
+// disc2d.cu
+int conv2d_k4_fwd(const float* x, const float* w, const float* b, int N, int Cin, int H, int W, int Cout, int stride,
+                  float slope, float* y, cudaStream_t stream);
+int conv2d_k4_dgrad(const float* dy, const float* w, int N, int Cin, int H, int W, int Cout, int stride, float* dx,
+                    cudaStream_t stream);
+int conv2d_k4_wgrad(const float* x, const float* dy, int N, int Cin, int H, int W, int Cout, int stride, float* dw,
+                    float* db, cudaStream_t stream);
+int in2d_lrelu_fwd(const float* x, int NC, int P, float eps, float slope, float* y, float* mean_rstd,
+                   cudaStream_t stream);
+int in2d_lrelu_bwd(const float* dy, const float* x, const float* mean_rstd, int NC, int P, float slope, float* dx,
+                   cudaStream_t stream);
+int lrelu_bwd(const float* dy, const float* y, long long n, float slope, float* dx, cudaStream_t stream);
+int loss_fwd(const float* p, const float* q, float target, long long n, int mode, float* loss, cudaStream_t stream);
+int loss_bwd(const float* p, const float* q, float target, long long n, int mode, const float* upstream, float* dp,
+             cudaStream_t stream);
+
 const char* last_error();
 
 }  // namespace nc
