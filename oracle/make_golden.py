@@ -16,7 +16,7 @@ from contextlib import redirect_stdout
 import numpy as np
 import torch
 
-from . import assemble, dice, geometry, mip, reference_harness as rh, unet
+from . import assemble, dice, discriminator, geometry, mip, reference_harness as rh, unet
 
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -141,6 +141,47 @@ def golden_mip():
     np.savez_compressed(os.path.join(GOLD, "mip_12.npz"), **out)
 
 
+GRAD_SAMPLE_STRIDE = 61
+
+
+def golden_discriminator():
+    """Reference define_D('basic', dimension=2) + GANLoss('lsgan') vs the oracle: prediction map, loss, and the
+    gradients w.r.t. the input image and every parameter, on a 44 x 36 image."""
+    rh.install()
+    from models import networks
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_D(1, 64, "basic", norm="instance", use_sigmoid=False, init_type="kaiming",
+                                init_gain=0.02, gpu_ids=[], dimension=2)
+    ref_sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in ref_sd.items()} == discriminator.STATE_DICT_SHAPES
+    assert sum(v.numel() for v in ref_sd.values()) == discriminator.N_PARAMS
+    sd = discriminator.random_state_dict(seed=0)
+    net.load_state_dict(sd)
+    crit = networks.GANLoss("lsgan")
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand((1, 1, 44, 36), generator=g).requires_grad_(True)
+    pred = net(x)
+    loss = crit(pred, True) * 0.5 + crit(pred, False) * 0.25
+    loss.backward()
+    out = {"x": x.detach().numpy(), "pred": pred.detach().numpy(), "loss": np.array(loss.item()),
+           "dx": x.grad.numpy()}
+    grads = {k: prm.grad.numpy() for k, prm in net.named_parameters()}
+    for k, gk in grads.items():      # 2.76 M gradient values: keep the norm and every 61st value of each tensor
+        out["dnorm_" + k] = np.array(np.linalg.norm(gk.astype(np.float64)))
+        out["dsample_" + k] = gk.reshape(-1)[::GRAD_SAMPLE_STRIDE].copy()
+    # oracle == reference
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.detach().clone().requires_grad_(True)
+    po = discriminator.discriminator_forward(xo, sdo)
+    lo = discriminator.lsgan_loss(po, True) * 0.5 + discriminator.lsgan_loss(po, False) * 0.25
+    lo.backward()
+    assert (po - pred).abs().max().item() <= 1e-6 and abs(lo.item() - loss.item()) <= 1e-7
+    assert (xo.grad - x.grad).abs().max().item() <= 1e-7
+    for k in sd:
+        assert np.abs(sdo[k].grad.numpy() - grads[k]).max() <= 1e-6 * (1 + np.abs(grads[k]).max()), k
+    np.savez_compressed(os.path.join(GOLD, "discriminator_44x36.npz"), **out)
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
@@ -149,6 +190,7 @@ def main():
     golden_dice_assemble()
     golden_unet()
     golden_mip()
+    golden_discriminator()
     print("golden vectors written to", GOLD)
 
 

@@ -100,3 +100,18 @@ def test_mip_matches_reference():
         np.random.set_state(state)
         proj, start = mip.get_projection(vol, 4, axis)
         assert start == int(f[f"start{axis}"]) and np.array_equal(proj.numpy(), f[f"proj{axis}"])
+
+
+def test_discriminator_matches_reference_module():
+    from oracle import discriminator as odisc
+    f = np.load(os.path.join(GOLDEN, "discriminator_44x36.npz"))
+    sd = {k: v.clone().requires_grad_(True) for k, v in odisc.random_state_dict(seed=0).items()}
+    assert sum(v.numel() for v in sd.values()) == odisc.N_PARAMS
+    x = torch.from_numpy(f["x"]).requires_grad_(True)
+    pred = odisc.discriminator_forward(x, sd)
+    loss = odisc.lsgan_loss(pred, True) * 0.5 + odisc.lsgan_loss(pred, False) * 0.25
+    loss.backward()
+    assert np.abs(pred.detach().numpy() - f["pred"]).max() <= 1e-6 and abs(loss.item() - float(f["loss"])) <= 1e-7
+    assert np.abs(x.grad.numpy() - f["dx"]).max() <= 1e-7
+    for k in sd:
+        assert np.abs(sd[k].grad.numpy().reshape(-1)[::61] - f["dsample_" + k]).max() <= 1e-6
