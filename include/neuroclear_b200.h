@@ -195,6 +195,11 @@ int nc_loss_fwd(const float* p, const float* q, float target, int64_t n, int32_t
 int nc_loss_bwd(const float* p, const float* q, float target, int64_t n, int32_t mode, const float* upstream,
                 float* dp, nc_stream_t stream);
 
+/* torch.optim.Adam step (apollo_model.py:131-136: lr, betas=(beta1, 0.999), eps 1e-8, no weight decay) for one
+ * parameter tensor: p, exp_avg m, exp_avg_sq v updated in place from gradient g; `step` counts from 1. */
+int nc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int32_t step, nc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nc_lrelu_bwd": (C.c_int, [vp, vp, i64, f32, vp, vp]),
     "nc_loss_fwd": (C.c_int, [vp, vp, f32, i64, i32, vp, vp]),
     "nc_loss_bwd": (C.c_int, [vp, vp, f32, i64, i32, vp, vp, vp]),
+    "nc_adam_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
 }
 
 _lib = None

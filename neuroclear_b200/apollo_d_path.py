@@ -1,0 +1,156 @@
+"""The projection / discriminator path of the reference's ``AxialToLateralGANApolloModel``
+(models/axial_to_lateral_gan_apollo_model.py) on the B200 kernels:
+
+* the four 2-D PatchGAN discriminators D_A_axial, D_A_lateral, D_B_axial, D_B_lateral (:99-123), created in the
+  reference's order so that seeded initialisation matches;
+* ``iter_f`` / ``proj_f`` (:310-320) on ``Volume`` — same host ``np.random`` draws in the same order;
+* the six discriminator losses ``backward_D_*`` (:169-253) and the discriminator update (:297-307) with a fused
+  Adam kernel (lr, betas=(beta1, 0.999));
+* the generator-side adversarial terms of ``backward_G`` (:255-276) as a differentiable function of ``fake`` and
+  ``rec`` (so that a generator's autograd can continue from them), and the cycle L1 term (:279).
+
+The generators' own forward/backward (G_A = unet_deconv training, G_B = deep_linear_gen) are not part of this
+module.
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import torch
+
+from . import discriminator
+from ._lib import call, f32, i64, ptr, stream_ptr
+from .projection import Volume
+
+
+class FusedAdam:
+    """torch.optim.Adam(params, lr, betas) semantics (no weight decay / amsgrad) on nc_adam_step."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.state = {}
+        self.step_count = 0
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        self.step_count += 1
+        for p in self.params:
+            if p.grad is None:
+                continue
+            st = self.state.get(p)
+            if st is None:
+                st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
+            g = p.grad.contiguous()
+            with torch.cuda.device(p.device):
+                call("nc_adam_step", ptr(p), ptr(g), ptr(st[0]), ptr(st[1]), i64(p.numel()), f32(self.lr),
+                     f32(self.betas[0]), f32(self.betas[1]), f32(self.eps), self.step_count, stream_ptr())
+            p.add_(0)   # the kernel wrote through a raw pointer: bump the version counter for autograd / caches
+
+
+class ApolloDiscriminatorPath:
+    def __init__(self, opt, device):
+        self.opt = opt
+        self.device = torch.device(device)
+        gpu_ids = [self.device.index if self.device.index is not None else 0]
+        mk = lambda nc: discriminator.define_D(nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, opt.init_type,
+                                               opt.init_gain, False, gpu_ids, dimension=2)
+        self.netD_A_axial = mk(opt.output_nc)      # creation order of apollo_model.py:99-123
+        self.netD_A_lateral = mk(opt.output_nc)
+        self.netD_B_axial = mk(opt.input_nc)
+        self.netD_B_lateral = mk(opt.input_nc)
+        self.criterionGAN = discriminator.GANLoss(opt.gan_mode).to(self.device)
+        self.criterionCycle = discriminator.L1Loss()
+        self.optimizer_D = FusedAdam(
+            itertools.chain(self.netD_A_axial.parameters(), self.netD_A_lateral.parameters(),
+                            self.netD_B_axial.parameters(), self.netD_B_lateral.parameters()),
+            lr=opt.lr, betas=(opt.beta1, 0.999))
+        s = float(sum(opt.lambda_plane))
+        self.lambda_plane_target, self.lambda_slice, self.lambda_proj = [f / s for f in opt.lambda_plane]
+        self.lateral_axis, self.axial_1_axis, self.axial_2_axis = 0, 1, 2
+        self.randomize_projection_depth = opt.randomize_projection_depth
+        self.projection_depth = opt.projection_depth
+
+    def discriminators(self):
+        return [self.netD_A_lateral, self.netD_A_axial, self.netD_B_lateral, self.netD_B_axial]
+
+    # ---- set_input (:142-160): the projection depth is drawn once per step
+    def draw_projection_depth(self):
+        if self.randomize_projection_depth:
+            self.projection_depth = np.random.randint(max(2, self.opt.min_projection_depth),
+                                                      self.opt.projection_depth + 1)
+        return self.projection_depth
+
+    # ---- :310-320
+    def iter_f(self, input, function, slice_axis):
+        return function(Volume(input, self.device).get_slice(slice_axis))
+
+    def proj_f(self, input, function, slice_axis):
+        return function(Volume(input, self.device).get_projection(self.projection_depth, slice_axis))
+
+    # ---- :169-229
+    def backward_D_slice(self, netD, real, fake, slice_axis_real, slice_axis_fake):
+        pred_real = self.iter_f(real, netD, slice_axis_real)
+        pred_fake = self.iter_f(fake.detach(), netD, slice_axis_fake)
+        loss_D = (self.criterionGAN(pred_real, True) + self.criterionGAN(pred_fake, False)) * 0.5
+        loss_D.backward()
+        return loss_D
+
+    def backward_D_projection(self, netD, real, fake, slice_axis_real, slice_axis_fake):
+        pred_real = self.iter_f(real, netD, slice_axis_real)
+        pred_fake = self.proj_f(fake.detach(), netD, slice_axis_fake)
+        loss_D = (self.criterionGAN(pred_real, True) + self.criterionGAN(pred_fake, False)) * 0.5
+        loss_D.backward()
+        return loss_D
+
+    # ---- :231-253
+    def backward_D_A_lateral(self, real, fake):
+        self.loss_D_A_lateral = self.backward_D_projection(self.netD_A_lateral, real, fake, 0, 0)
+
+    def backward_D_A_axial(self, real, fake):
+        self.loss_D_A_axial_1 = self.backward_D_projection(self.netD_A_axial, real, fake, 0, 1)
+        self.loss_D_A_axial_2 = self.backward_D_projection(self.netD_A_axial, real, fake, 0, 2)
+        self.loss_D_A_axial = (self.loss_D_A_axial_1 + self.loss_D_A_axial_2) * 0.5
+
+    def backward_D_B_lateral(self, real, rec):
+        self.loss_D_B_lateral = self.backward_D_slice(self.netD_B_lateral, real, rec, 0, 0)
+
+    def backward_D_B_axial(self, real, rec):
+        self.loss_D_B_axial_1 = self.backward_D_slice(self.netD_B_axial, real, rec, 1, 1)
+        self.loss_D_B_axial_2 = self.backward_D_slice(self.netD_B_axial, real, rec, 2, 2)
+        self.loss_D_B_axial = (self.loss_D_B_axial_1 + self.loss_D_B_axial_2) * 0.5
+
+    # ---- discriminator half of optimize_parameters (:297-307)
+    def optimize_D(self, real, fake, rec):
+        for net in self.discriminators():
+            for p in net.parameters():
+                p.requires_grad_(True)
+        self.optimizer_D.zero_grad()
+        self.backward_D_A_lateral(real, fake)
+        self.backward_D_A_axial(real, fake)
+        self.backward_D_B_lateral(real, rec)
+        self.backward_D_B_axial(real, rec)
+        self.optimizer_D.step()
+
+    # ---- generator-side terms of backward_G (:255-281); Ds are frozen (set_requires_grad(..., False), :291-292)
+    def generator_losses(self, real, fake, rec):
+        for net in self.discriminators():
+            for p in net.parameters():
+                p.requires_grad_(False)
+        g = self.criterionGAN
+        self.loss_G_A_lateral = g(self.proj_f(fake, self.netD_A_lateral, 0), True) * self.lambda_plane_target
+        self.loss_G_A_axial = g(self.proj_f(fake, self.netD_A_axial, 1), True) * self.lambda_slice + \
+            g(self.proj_f(fake, self.netD_A_axial, 2), True) * self.lambda_slice
+        self.loss_G_A = self.loss_G_A_lateral + self.loss_G_A_axial * 0.5
+        self.loss_G_B_lateral = g(self.iter_f(rec, self.netD_B_lateral, 0), True) * self.lambda_plane_target
+        self.loss_G_B_axial = g(self.iter_f(rec, self.netD_B_axial, 1), True) * self.lambda_slice + \
+            g(self.iter_f(rec, self.netD_B_axial, 2), True) * self.lambda_slice
+        self.loss_G_B = self.loss_G_B_lateral + self.loss_G_B_axial * 0.5
+        self.loss_cycle = self.criterionCycle(rec, real) * self.opt.lambda_A
+        self.loss_G = self.loss_G_A + self.loss_G_B + self.loss_cycle
+        return self.loss_G

@@ -173,4 +173,9 @@ int nc_loss_bwd(const float* p, const float* q, float target, int64_t n, int32_t
   return loss_bwd(p, q, target, n, mode, upstream, dp, S(stream));
 }
 
+int nc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int32_t step, nc_stream_t stream) {
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, S(stream));
+}
+
 }  // extern "C"

@@ -286,4 +286,30 @@ int loss_bwd(const float* p, const float* q, float target, long long n, int mode
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam (apollo_model.py:131-136; no weight decay, no amsgrad), one launch per parameter tensor:
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float beta1, float beta2, float step_size,
+                                 float inv_sqrt_bc2, float eps) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    const float gi = g[i];
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+              int step, cudaStream_t stream) {
+  if (step < 1) return set_error("adam_step: step counts from 1");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step), bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const int blocks = static_cast<int>((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  adam_step_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, n, beta1, beta2, static_cast<float>(lr / bc1),
+                                               static_cast<float>(1.0 / sqrt(bc2)), eps);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace nc

@@ -93,6 +93,9 @@ int loss_fwd(const float* p, const float* q, float target, long long n, int mode
 int loss_bwd(const float* p, const float* q, float target, long long n, int mode, const float* upstream, float* dp,
              cudaStream_t stream);
 
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+              int step, cudaStream_t stream);
+
 const char* last_error();
 
 }  // namespace nc

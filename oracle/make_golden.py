@@ -182,6 +182,67 @@ def golden_discriminator():
     np.savez_compressed(os.path.join(GOLD, "discriminator_44x36.npz"), **out)
 
 
+def apollo_opt(**kw):
+    from argparse import Namespace
+    o = dict(isTrain=True, gpu_ids=[], checkpoints_dir="/tmp/nc_golden_ckpt", name="golden", preprocess="none",
+             gan_mode="lsgan", image_dimension=3, randomize_projection_depth=True, projection_depth=10,
+             min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1, ngf=64, ndf=64,
+             netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3, norm="instance", no_dropout=True,
+             init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1, direction="AtoB", lambda_A=5.0,
+             lr_policy="constant")
+    o.update(kw)
+    return Namespace(**o)
+
+
+D_NAMES = ["D_A_axial", "D_A_lateral", "D_B_axial", "D_B_lateral"]   # creation order, apollo_model.py:99-123
+
+
+def golden_apollo_discriminator_path():
+    """The REFERENCE AxialToLateralGANApolloModel on a 32^3 crop (CPU): its real / fake / rec volumes, then
+    (1) the discriminator half of optimize_parameters() (six D losses, Adam step) and (2) backward_G()'s losses and
+    gradients w.r.t. fake and rec — both with a fixed np.random seed, D weights from the oracle's seeded state dicts."""
+    rh.install()
+    from models.axial_to_lateral_gan_apollo_model import AxialToLateralGANApolloModel
+    with redirect_stdout(io.StringIO()):
+        m = AxialToLateralGANApolloModel(apollo_opt())
+    for i, name in enumerate(D_NAMES):
+        getattr(m, "net" + name).load_state_dict(discriminator.random_state_dict(seed=10 + i))
+    np.random.seed(0)
+    real = torch.rand((1, 1, 32, 32, 32), generator=torch.Generator().manual_seed(0))
+    m.set_input({"A": real, "A_paths": "golden"})
+    with torch.no_grad():
+        m.forward()
+    rec = (m.rec - m.rec.mean()) / m.rec.std() * 0.2 + 0.5      # G_B is un-normalised at init: keep rec in a sane range
+    out = {"real": real.numpy(), "fake": m.fake.numpy(), "rec": rec.numpy(), "depth": np.array(m.projection_depth)}
+    # ---- (2) generator-side terms first (Ds untouched): leaf copies of fake / rec collect the gradients
+    m.fake = m.fake.detach().clone().requires_grad_(True)
+    m.rec = rec.detach().clone().requires_grad_(True)
+    m.set_requires_grad([m.netD_A_lateral, m.netD_A_axial, m.netD_B_lateral, m.netD_B_axial], False)
+    np.random.seed(9)
+    m.backward_G()
+    for k in ("G_A", "G_A_lateral", "G_A_axial", "G_B", "G_B_lateral", "G_B_axial", "cycle"):
+        out["loss_" + k] = np.array(float(getattr(m, "loss_" + k)))
+    out["dfake"], out["drec"] = m.fake.grad.numpy(), m.rec.grad.numpy()
+    # ---- (1) discriminator step
+    m.set_requires_grad([m.netD_A_lateral, m.netD_A_axial, m.netD_B_lateral, m.netD_B_axial], True)
+    m.optimizer_D.zero_grad()
+    np.random.seed(7)
+    m.backward_D_A_lateral()
+    m.backward_D_A_axial()
+    m.backward_D_B_lateral()
+    m.backward_D_B_axial()
+    for k in ("D_A_lateral", "D_A_axial", "D_B_lateral", "D_B_axial"):
+        out["loss_" + k] = np.array(float(getattr(m, "loss_" + k)))
+    for name in D_NAMES:
+        for k, prm in getattr(m, "net" + name).named_parameters():
+            out["grad_%s.%s" % (name, k)] = prm.grad.numpy().reshape(-1)[::GRAD_SAMPLE_STRIDE].copy()
+    m.optimizer_D.step()
+    for name in D_NAMES:
+        for k, prm in getattr(m, "net" + name).named_parameters():
+            out["after_%s.%s" % (name, k)] = prm.detach().numpy().reshape(-1)[::GRAD_SAMPLE_STRIDE].copy()
+    np.savez_compressed(os.path.join(GOLD, "apollo_d_path_32.npz"), **out)
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
@@ -191,6 +252,7 @@ def main():
     golden_unet()
     golden_mip()
     golden_discriminator()
+    golden_apollo_discriminator_path()
     print("golden vectors written to", GOLD)
 
 
