@@ -10,6 +10,55 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def data_parallel_discriminator_step(rank, world, dev):
+    """an N-GPU discriminator step == a single-process step on the same N crops with the
+    gradients averaged.  Every rank also replays all crops locally and compares the updated parameters."""
+    import io
+    from argparse import Namespace
+    from contextlib import redirect_stdout
+    from neuroclear_b200.apollo_d_path import ApolloDiscriminatorPath
+    from oracle import discriminator as odisc
+    opt = Namespace(gan_mode="lsgan", randomize_projection_depth=False, projection_depth=6, min_projection_depth=2,
+                    lambda_plane=[1, 1, 1], input_nc=1, output_nc=1, ndf=64, netD="basic", n_layers_D=3,
+                    norm="instance", init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1, lambda_A=5.0)
+    names = ["D_A_axial", "D_A_lateral", "D_B_axial", "D_B_lateral"]
+
+    def make(distributed):
+        with redirect_stdout(io.StringIO()):
+            p = ApolloDiscriminatorPath(opt, dev, distributed=distributed)
+        for i, n in enumerate(names):
+            getattr(p, "net" + n).module.load_state_dict(odisc.random_state_dict(seed=20 + i))
+        return p
+
+    def crops(r):
+        g = torch.Generator().manual_seed(100 + r)
+        return [torch.rand((1, 1, 32, 32, 32), generator=g).to(dev) for _ in range(3)]
+
+    dp = make(True)
+    np.random.seed(50 + rank)
+    dp.optimize_D(*crops(rank))
+    # single-process replay: gradients of every crop (same per-rank RNG streams), averaged, one Adam step
+    sp = make(False)
+    params = sp.optimizer_D.params
+    acc = [torch.zeros_like(p) for p in params]
+    for r in range(world):
+        sp.optimizer_D.zero_grad()
+        np.random.seed(50 + r)
+        real, fake, rec = crops(r)
+        sp.backward_D_A_lateral(real, fake)
+        sp.backward_D_A_axial(real, fake)
+        sp.backward_D_B_lateral(real, rec)
+        sp.backward_D_B_axial(real, rec)
+        for a, p in zip(acc, params):
+            a += p.grad
+    for a, p in zip(acc, params):
+        p.grad = a / world
+    sp.optimizer_D.step()
+    worst = max((a.detach() - b.detach()).abs().max().item() for a, b in zip(dp.optimizer_D.params, params))
+    print("rank %d/%d data-parallel D step vs single-process replay: max |dparam| %.3g" % (rank, world, worst), flush=True)
+    return worst <= 2e-6
+
+
 def main():
     from neuroclear_b200.pipeline import DicedInference
     from oracle import unet as ounet
@@ -32,6 +81,7 @@ def main():
         print("rank %d/%d shape %s slab [%d,%d): identical=%s percentiles_identical=%s" %
               (rank, world, shape, z0, z1, same, pc), flush=True)
         ok = ok and same and pc
+    ok = data_parallel_discriminator_step(rank, world, dev) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

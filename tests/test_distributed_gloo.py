@@ -80,3 +80,30 @@ def test_three_rank_uneven(tmp_path):
     world = 3
     mp.spawn(_worker, args=(world, _free_port(), (50, 20, 33), 16, 4, 1, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def _grad_worker(rank, world, port, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neuroclear_b200.apollo_d_path import allreduce_mean_gradients
+        g = torch.Generator().manual_seed(0)
+        shapes = [(64, 1, 4, 4), (64,), (128, 64, 4, 4), (7,)]
+        params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+        all_grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(world)]   # same on every rank
+        for p, gr in zip(params[:3], all_grads[rank][:3]):      # the last parameter has no gradient on any rank
+            p.grad = gr.clone()
+        allreduce_mean_gradients(params)
+        for i, p in enumerate(params[:3]):
+            want = sum(all_grads[r][i] for r in range(world)) / world
+            assert torch.allclose(p.grad, want, atol=1e-6)
+        assert params[3].grad is None
+        open(os.path.join(result_dir, "gok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("gok%d" % r)).exists() for r in range(world))
