@@ -93,6 +93,74 @@ int nc_conv3d_k3_fwd(const void* x_f16, const float* in_mean_rstd, int32_t nb, i
                      int32_t cin, const void* packed, int32_t cout, void* y_raw, float* stats_partial,
                      nc_stream_t stream);
 
+/* ---- training: gradients of the same Conv3d layers (what autograd computes for networks.py:413-538 when
+ * train_onecube.py / axial_to_lateral_gan_apollo_model.py:255-295 call backward) -------------------------------------
+ * Gradient tensors are bf16 NDHWC (fp16 would underflow: d loss / d voxel ~ 1e-6), accumulation is fp32.
+ *
+ * nc_conv3d_k3_dgrad: dx = conv(dy, filter transposed over channels and flipped in space) on the forward tcgen05
+ *   kernel.  dy: bf16 (NB,D,H,W,Cout); packed: nc_pack_weights_conv3d_k3_dgrad image (bf16, same size as the forward
+ *   image); dx: bf16 (NB,D,H,W,Cin).  Cout % 64 == 0, Cin in {64,128k}.
+ * nc_conv3d_wgrad: dW[co][ci][kd][kh][kw] = sum_v dy[v][co] * x[v + tap - pad][ci], tcgen05 GEMM whose K dimension
+ *   is the voxel (both operands read MN-major from TMA-staged halo planes), split-K over the CTAs with a fixed-order
+ *   (deterministic) reduction.  x: 16-bit NDHWC (NB,D,H,W,Cin), x_fmt 0 = fp16 / 1 = bf16 (the forward activations
+ *   are fp16); dy likewise (dy_fmt).  ks in {3,5} (Unet_deconv k3; DeepLinearGenerator k5 / k3, networks.py:899-905).
+ *   scratch: nc_conv3d_wgrad_scratch_bytes(...) bytes; dw: float32 OIDHW (Cout,Cin,ks,ks,ks), overwritten. */
+int nc_pack_weights_conv3d_k3_dgrad(const float* w_oidhw, int32_t cout, int32_t cin, void* packed,
+                                    nc_stream_t stream);
+int nc_conv3d_k3_dgrad(const void* dy_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cout,
+                       const void* packed, int32_t cin, void* dx_bf16, nc_stream_t stream);
+int64_t nc_conv3d_wgrad_scratch_bytes(int32_t ks, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
+                                      int32_t cout);
+int nc_conv3d_wgrad(const void* x, int32_t x_fmt, const void* dy, int32_t dy_fmt, int32_t nb, int32_t d, int32_t h,
+                    int32_t w, int32_t cin, int32_t cout, int32_t ks, void* scratch, float* dw, nc_stream_t stream);
+
+/* Backward of ConvTranspose3d(k2, s2) (networks.py:500,503) as two plain GEMMs over a space-to-depth gather of the
+ * output gradient: g[coarse voxel][tap * Cout + co] = dy[2 * voxel + tap][y_coff + co], tap = (a*2+b)*2+c.
+ *   data gradient:   dx = nc_conv3d_k1_bf16(g, K = 8*Cout, packed = nc_pack_weights_convT3d_k2s2_dgrad image, N = Cin)
+ *   weight gradient: nc_conv3d_wgrad(x, g, ks = 1, cin = Cin, cout = 8*Cout) -> (8*Cout, Cin) = dW[ci][co][tap]^T
+ *   bias gradient:   nc_colsum_bf16 over dy. */
+int nc_space_to_depth_bf16(const void* src_bf16, int32_t ld, int32_t coff, int32_t nb, int32_t d_coarse,
+                           int32_t h_coarse, int32_t w_coarse, int32_t c, void* out_bf16, nc_stream_t stream);
+int nc_pack_weights_convT3d_k2s2_dgrad(const float* w_iodhw, int32_t cin, int32_t cout, void* packed,
+                                       nc_stream_t stream);
+int nc_conv3d_k1_bf16(const void* x_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t k, const void* packed,
+                      int32_t n, void* y_bf16, nc_stream_t stream);
+/* out[c] = sum over all nb * rows rows of src[row][coff + c] (bf16 in, fixed-order fp64 reduction). */
+int nc_colsum_bf16(const void* src_bf16, int32_t ld, int32_t coff, int32_t nb, int64_t rows, int32_t c, void* scratch,
+                   float* out, nc_stream_t stream);
+/* fp16 -> bf16 copy of a channel slice of an NDHWC tensor (rows voxels). */
+int nc_cast_f16_bf16(const void* src_f16, int32_t src_ld, int32_t src_coff, int64_t rows, int32_t c, void* dst_bf16,
+                     int32_t dst_ld, int32_t dst_coff, nc_stream_t stream);
+
+/* Scratch for the reductions of the backward kernels below (one buffer serves them all). */
+int64_t nc_bwd_scratch_bytes(int32_t nb);
+/* nc_in_relu_apply with bf16 output: the weight-gradient GEMM reads activations in the gradient's format. */
+int nc_in_relu_apply_bf16(const void* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+                          int32_t c, void* y_bf16, int32_t y_ld, int32_t y_coff, void* pooled_bf16,
+                          nc_stream_t stream);
+/* Backward of InstanceNorm3d(affine=False) + ReLU (networks.py:422-423 etc.) of one layer:
+ *   yhat = (raw - mean) * rstd, g = dA * [yhat > 0], d_raw = rstd * (g - mean_v(g) - yhat * mean_v(g * yhat)).
+ * dA (gradient w.r.t. the activation) comes from, by `mode`:
+ *   0: the bf16 tensor `grad` (row pitch grad_ld, channel offset grad_coff);
+ *   1: the head: dA[v][c] = du[v] * w_head[c] (nc_head_1x1_sigmoid_bwd);
+ *   2: skip + pool: grad slice as in 0 PLUS the MaxPool3d(2) routing of `dpool` (bf16 (NB,D/2,H/2,W/2,C)) to the
+ *      first maximum of every 2x2x2 window — the gradient of `torch.cat([conv, up])` + `maxpool(conv)`.
+ * m12: float32 (NB,2,C) work buffer (the two means); d_raw: bf16 (NB,D,H,W,C). */
+int nc_in_relu_bwd(const void* raw_f16, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t c,
+                   int32_t mode, const void* grad_bf16, int32_t grad_ld, int32_t grad_coff, const float* du,
+                   const float* w_head, const void* dpool_bf16, void* scratch, float* m12, void* d_raw_bf16,
+                   nc_stream_t stream);
+/* Backward of the head (networks.py:507-510,536): given dout = dL/d sigmoid output (float32 (NB,D,H,W)):
+ * du = dout * out * (1 - out) * w2 (float32 per voxel) and grads (68 floats) = [d one_by_one.weight (64) |
+ * d one_by_one.bias | d one_by_one_2.weight | d one_by_one_2.bias | 0], summed over the samples. */
+int nc_head_1x1_sigmoid_bwd(const void* raw_f16, const float* mean_rstd, const float* head_params, const float* dout,
+                            int32_t nb, int32_t d, int32_t h, int32_t w, float* du, void* scratch, float* grads,
+                            nc_stream_t stream);
+/* Weight gradient of the Cin = 1 first conv (networks.py:420): dw float32 (64, 27). x float32 (NB,D,H,W),
+ * dy bf16 (NB,D,H,W,64). */
+int nc_conv3d_cin1_k3_wgrad(const float* x, const void* dy_bf16, int32_t nb, int32_t d, int32_t h, int32_t w,
+                            void* scratch, float* dw, nc_stream_t stream);
+
 /* nn.ConvTranspose3d(Cin -> Cout, k2 s2) t_conv2 / t_conv1 (networks.py:500,503) fused with the channel concat
  * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as fp16 into
  * channels [y_coff, y_coff+Cout) of an NDHWC buffer (NB,2D,2H,2W,y_ld). */

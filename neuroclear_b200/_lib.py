@@ -31,6 +31,20 @@ SIGNATURES = {
     "nc_pack_weights_conv3d_k3": (C.c_int, [vp, i32, i32, vp, vp]),
     "nc_pack_weights_convT3d_k2s2": (C.c_int, [vp, i32, i32, vp, vp]),
     "nc_conv3d_k3_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
+    "nc_pack_weights_conv3d_k3_dgrad": (C.c_int, [vp, i32, i32, vp, vp]),
+    "nc_conv3d_k3_dgrad": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp]),
+    "nc_conv3d_wgrad_scratch_bytes": (i64, [i32, i32, i32, i32, i32, i32, i32]),
+    "nc_conv3d_wgrad": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "nc_space_to_depth_bf16": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "nc_pack_weights_convT3d_k2s2_dgrad": (C.c_int, [vp, i32, i32, vp, vp]),
+    "nc_conv3d_k1_bf16": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp]),
+    "nc_colsum_bf16": (C.c_int, [vp, i32, i32, i32, i64, i32, vp, vp, vp]),
+    "nc_cast_f16_bf16": (C.c_int, [vp, i32, i32, i64, i32, vp, i32, i32, vp]),
+    "nc_bwd_scratch_bytes": (i64, [i32]),
+    "nc_in_relu_apply_bf16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "nc_in_relu_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "nc_head_1x1_sigmoid_bwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "nc_conv3d_cin1_k3_wgrad": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "nc_convT3d_k2s2_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
     "nc_in_stats_scratch_bytes": (i64, [i32, i32]),
     "nc_in_stats_finalize": (C.c_int, [vp, i32, i64, i32, i64, f32, vp, vp, vp]),

@@ -7,7 +7,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SOURCES = ["runtime.cu", "conv3d_tc.cu", "conv1_tc.cu", "elementwise.cu", "disc2d.cu", "api.cu"]
+SOURCES = ["runtime.cu", "conv3d_tc.cu", "wgrad3d_tc.cu", "conv1_tc.cu", "elementwise.cu", "unet_bwd.cu", "disc2d.cu", "api.cu"]
 HEADERS = ["internal.h", "ptx.cuh"]
 OUT = os.path.join(_HERE, "libneuroclear_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -34,15 +34,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_probe() -> str:
-    """The standalone hardware probe (tests/cuda/probe_conv.cu) used by tests/cuda/run_probe.sh."""
+    """The standalone hardware probes (tests/cuda/probe_conv.cu, probe_grad.cu) used by tests/cuda/run_probe*.sh."""
     out_dir = os.path.join(_ROOT, "build")
     os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "probe_conv")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler", "-fopenmp",
-                    "-o", out, os.path.join(_ROOT, "tests", "cuda", "probe_conv.cu"), "-L", _HERE,
-                    "-lneuroclear_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../neuroclear_b200"], check=True)
-    return out
+    for name in ("probe_conv", "probe_grad"):
+        out = os.path.join(out_dir, name)
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler",
+                        "-fopenmp", "-o", out, os.path.join(_ROOT, "tests", "cuda", name + ".cu"), "-L", _HERE,
+                        "-lneuroclear_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../neuroclear_b200"],
+                       check=True)
+    return os.path.join(out_dir, "probe_conv")
 
 
 if __name__ == "__main__":

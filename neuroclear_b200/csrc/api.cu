@@ -79,6 +79,61 @@ int nc_conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int32_t nb, int32
                      nc_stream_t stream) {
   return conv3d_k3_fwd(x, in_mean_rstd, nb, d, h, w, cin, packed, cout, y_raw, stats_partial, S(stream));
 }
+int nc_pack_weights_conv3d_k3_dgrad(const float* w, int32_t cout, int32_t cin, void* packed, nc_stream_t stream) {
+  return pack_weights_dgrad(w, packed, cout, cin, S(stream));
+}
+int nc_conv3d_k3_dgrad(const void* dy, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cout, const void* packed,
+                       int32_t cin, void* dx, nc_stream_t stream) {
+  return conv3d_k3_dgrad(dy, nb, d, h, w, cout, packed, cin, dx, S(stream));
+}
+int64_t nc_conv3d_wgrad_scratch_bytes(int32_t ks, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t cin,
+                                      int32_t cout) {
+  return static_cast<int64_t>(conv3d_wgrad_scratch_bytes(ks, nb, d, h, w, cin, cout));
+}
+int nc_conv3d_wgrad(const void* x, int32_t x_fmt, const void* dy, int32_t dy_fmt, int32_t nb, int32_t d, int32_t h,
+                    int32_t w, int32_t cin, int32_t cout, int32_t ks, void* scratch, float* dw, nc_stream_t stream) {
+  return conv3d_wgrad(x, x_fmt, dy, dy_fmt, nb, d, h, w, cin, cout, ks, scratch, dw, S(stream));
+}
+int nc_pack_weights_convT3d_k2s2_dgrad(const float* w, int32_t cin, int32_t cout, void* packed, nc_stream_t stream) {
+  return pack_weights_convT_dgrad(w, packed, cin, cout, S(stream));
+}
+int nc_conv3d_k1_bf16(const void* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t k, const void* packed,
+                      int32_t n, void* y, nc_stream_t stream) {
+  return conv3d_k1_bf16(x, nb, d, h, w, k, packed, n, y, S(stream));
+}
+int nc_in_relu_apply_bf16(const void* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
+                          int32_t c, void* y, int32_t y_ld, int32_t y_coff, void* pooled, nc_stream_t stream) {
+  return in_relu_apply_bf16(raw, mean_rstd, nb, d, h, w, c, y, y_ld, y_coff, pooled, S(stream));
+}
+int64_t nc_bwd_scratch_bytes(int32_t nb) { return static_cast<int64_t>(bwd_blocks()) * nb * 512 * 4; }
+int nc_in_relu_bwd(const void* raw, const float* mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t c,
+                   int32_t mode, const void* grad, int32_t grad_ld, int32_t grad_coff, const float* du,
+                   const float* w_head, const void* dpool, void* scratch, float* m12, void* d_raw,
+                   nc_stream_t stream) {
+  return in_relu_bwd(raw, mean_rstd, nb, d, h, w, c, mode, grad, grad_ld, grad_coff, du, w_head, dpool,
+                     static_cast<float*>(scratch), m12, d_raw, S(stream));
+}
+int nc_head_1x1_sigmoid_bwd(const void* raw, const float* mean_rstd, const float* hp, const float* dout, int32_t nb,
+                            int32_t d, int32_t h, int32_t w, float* du, void* scratch, float* grads,
+                            nc_stream_t stream) {
+  return head_bwd(raw, mean_rstd, hp, dout, nb, d, h, w, du, static_cast<float*>(scratch), grads, S(stream));
+}
+int nc_conv3d_cin1_k3_wgrad(const float* x, const void* dy, int32_t nb, int32_t d, int32_t h, int32_t w,
+                            void* scratch, float* dw, nc_stream_t stream) {
+  return conv1_wgrad(x, dy, nb, d, h, w, static_cast<float*>(scratch), dw, S(stream));
+}
+int nc_space_to_depth_bf16(const void* src, int32_t ld, int32_t coff, int32_t nb, int32_t d, int32_t h, int32_t w,
+                           int32_t c, void* out, nc_stream_t stream) {
+  return space_to_depth_bf16(src, ld, coff, nb, d, h, w, c, out, S(stream));
+}
+int nc_colsum_bf16(const void* src, int32_t ld, int32_t coff, int32_t nb, int64_t rows, int32_t c, void* scratch,
+                   float* out, nc_stream_t stream) {
+  return colsum_bf16(src, ld, coff, nb, rows, c, static_cast<float*>(scratch), out, S(stream));
+}
+int nc_cast_f16_bf16(const void* src, int32_t src_ld, int32_t src_coff, int64_t rows, int32_t c, void* dst,
+                     int32_t dst_ld, int32_t dst_coff, nc_stream_t stream) {
+  return cast_f16_bf16(src, src_ld, src_coff, rows, c, dst, dst_ld, dst_coff, S(stream));
+}
 int nc_convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
                         int32_t cin, const void* packed, const float* bias, int32_t cout, void* y, int32_t y_ld,
                         int32_t y_coff, nc_stream_t stream) {

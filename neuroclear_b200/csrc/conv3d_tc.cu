@@ -22,6 +22,7 @@
 //     the fp32 accumulators (InstanceNorm statistics, reduced deterministically later);
 //     MODE 1: transposed conv — + bias, fp16 tile staged in shared memory and written by a TMA store whose tensor
 //     map walks the fine grid with element stride 2 (pixel shuffle) into a channel slice of the concat buffer.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "internal.h"
@@ -116,6 +117,17 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// fp32 pair -> packed bf16x2 (bf16 shares fp32's exponent range: no saturation needed)
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack_pair(float a, float b) {
+  if constexpr (BF16) return pack_bf162(a, b);
+  return pack_half2_sat(a, b);
+}
+
 // Column sums over the 32 lanes of a warp for 32 per-lane values: afterwards lane l holds sum_lanes v[l].
 // Recursive halving: 16+8+4+2+1 shuffles instead of 32 x 5.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -137,7 +149,9 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // to fp16 — before handing it to the MMA warp.  Rows outside the volume were zero-filled by TMA and are left
 // untouched, which is exactly the conv's zero padding of the NORMALISED tensor.  This removes the separate
 // read-raw / write-normalised pass between two convolutions.
-template <int KS, int BN, int TD, int MODE, bool STACK, bool XF>
+// BF16: operands and output are bf16 and no statistics are taken — the data-gradient pass of the same convolution
+// (gradients need bf16's exponent range; see conv3d_k3_dgrad).
+template <int KS, int BN, int TD, int MODE, bool STACK, bool XF, bool BF16 = false>
 __global__ void __launch_bounds__(XF ? 384 : 256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapOut,
                  const ConvTcArgs args) {
@@ -245,7 +259,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     // The whole warp walks the (warp-uniform) loops so that every address / descriptor lives in uniform
     // registers; one elected lane issues the tcgen05 instructions.  (Issuing from a divergent single-lane
     // region makes the compiler broadcast each operand through R2UR per MMA, which costs more than the MMA.)
-    constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN);
+    constexpr uint32_t FMT = BF16 ? ((1u << 7) | (1u << 10)) : 0u;  // A / B operand format: 0 = fp16, 1 = bf16
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN) | FMT;
     // high descriptor words are constant: SBO [32,46), version 1 at bit 46, SWIZZLE_128B (2) at [61,64)
     constexpr uint32_t A_HI = ((C::HALO_W * 128u) >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -265,8 +280,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
       const uint32_t acc0 = tmem_base + buf * C::ACC_COLS;
       for (int c = 0; c < args.chunks; ++c) {
         if constexpr (STACK) {
-          constexpr uint32_t idesc64 = ptx::make_idesc_f16(128, 64), idesc128 = ptx::make_idesc_f16(128, 128),
-                             idesc192 = ptx::make_idesc_f16(128, 192);
+          constexpr uint32_t idesc64 = ptx::make_idesc_f16(128, 64) | FMT,
+                             idesc128 = ptx::make_idesc_f16(128, 128) | FMT,
+                             idesc192 = ptx::make_idesc_f16(128, 192) | FMT;
           for (int phase = 0; phase < 2; ++phase) {
             for (int i = 0; i < 3; ++i) {
               int s = pslot + 3 * phase + i;
@@ -535,20 +551,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                   co);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                dst[i] = make_uint4(pack_half2_sat(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
-                                    pack_half2_sat(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
-                                    pack_half2_sat(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
-                                    pack_half2_sat(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
+                dst[i] = make_uint4(pack_pair<BF16>(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
+                                    pack_pair<BF16>(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
+                                    pack_pair<BF16>(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
+                                    pack_pair<BF16>(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
             }
-            float v[32], v2[32];
+            if constexpr (!BF16) {
+              float v[32], v2[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = valid_hw ? __uint_as_float(raw[i]) : 0.f;
-              v[i] = x;
-              v2[i] = x * x;
+              for (int i = 0; i < 32; ++i) {
+                const float x = valid_hw ? __uint_as_float(raw[i]) : 0.f;
+                v[i] = x;
+                v2[i] = x * x;
+              }
+              csum[cc] += warp_colsum32(v, lane);
+              csq[cc] += warp_colsum32(v2, lane);
             }
-            csum[cc] += warp_colsum32(v, lane);
-            csq[cc] += warp_colsum32(v2, lane);
           }
         }
       }
@@ -557,7 +575,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&accEmpty[buf]);
 
-      if constexpr (MODE == 0) {
+      if constexpr (MODE == 0 && !BF16) {
         // lane l of warp q holds the column-l sums of its 32 rows; combine the 4 warps in fixed order
         float* mine = statScratch + q * 2 * BN;
 #pragma unroll
@@ -593,8 +611,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 // conv:  w is OIDHW fp32 (Cout, Cin, k, k, k); GEMM column n = output channel.
 // convT: w is IODHW fp32 (Cin, Cout, 2, 2, 2); GEMM column n = tap * Cout + co with tap = (a*2+b)*2+c.
 // stacked (conv, Cout = 64): [chunk][kh*3+kw][row = (2-kd)*64 + co][128 B], i.e. stages of 192 rows [kd2|kd1|kd0].
-__global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
-                                    int taps, int BN, int transposed, int stacked) {
+// dgrad: the data gradient of a stride-1 "same" conv is the conv of dy with the channel-transposed, spatially
+//        flipped filter: here Cout / Cin are the GEMM's N / K = the layer's Cin / Cout, w is still the layer's OIDHW
+//        tensor, and the image is written as bf16.
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin,
+                                    int taps, int BN, int transposed, int stacked, int dgrad) {
   const int chunks = Cin / 64;
   const int ngemm = transposed ? 8 * Cout : Cout;
   const int gtaps = transposed ? 1 : taps;
@@ -612,7 +633,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
     const int n = n_tile * BN + r;
     const int ci = chunk * 64 + k;
     float v;
-    if (!transposed) {
+    if (dgrad) {
+      v = w[(static_cast<size_t>(ci) * Cout + n) * taps + (taps - 1 - tap)];
+    } else if (!transposed) {
       v = w[(static_cast<size_t>(n) * Cin + ci) * taps + tap];
     } else {
       const int t8 = n / Cout, co = n - t8 * Cout;
@@ -628,12 +651,19 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
       const size_t stage = (static_cast<size_t>(n_tile) * chunks + chunk) * gtaps + tap;
       off = stage * BN * 64 + static_cast<size_t>(r) * 64 + ((((k >> 3) ^ (r & 7)) << 3) | (k & 7));
     }
-    out[off] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    if (dgrad) {
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      out[off] = *reinterpret_cast<const uint16_t*>(&b);
+    } else {
+      const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      out[off] = *reinterpret_cast<const uint16_t*>(&hv);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int D, int NB, int boxW, int boxH) {
+static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, int D, int NB, int boxW, int boxH,
+                         bool bf16 = false) {
   auto encode = get_tensor_map_encoder();
   if (!encode) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)NB};
@@ -641,8 +671,9 @@ static int make_act_tmap(CUtensorMap* m, const void* base, int C, int W, int H, 
                            (cuuint64_t)D * H * W * C * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)boxW, (cuuint32_t)boxH, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
+                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
@@ -668,10 +699,10 @@ static int make_convT_out_tmap(CUtensorMap* m, const void* base, int ld, int W2,
   return 0;
 }
 
-template <int KS, int BN, int TD, int MODE, bool STACK, bool XF>
+template <int KS, int BN, int TD, int MODE, bool STACK, bool XF, bool BF16 = false>
 static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvTcArgs& a, int smem_bytes,
                       cudaStream_t stream) {
-  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK, XF>;
+  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK, XF, BF16>;
   static bool attr_set[64] = {false};
   if (first_use_on_device(attr_set))
     NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -682,11 +713,11 @@ static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvT
   return 0;
 }
 
-template <int KS, int BN, int TD, int MODE, bool STACK = false>
+template <int KS, int BN, int TD, int MODE, bool STACK = false, bool BF16 = false>
 static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
   using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
   CUtensorMap tm, tmo;
-  if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H)) return rc;
+  if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H, BF16)) return rc;
   if constexpr (MODE == 1) {
     if (int rc = make_convT_out_tmap(&tmo, a.out_f16, a.ld1, 2 * a.W, 2 * a.H, 2 * a.D, a.NB)) return rc;
   } else {
@@ -697,8 +728,12 @@ static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream)
   a.tiles_d = (a.D + TD - 1) / TD;
   a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
   a.cin_total = Cin;
-  if (a.in_mr) return launch_one<KS, BN, TD, MODE, STACK, true>(tm, tmo, a, C::SMEM_BYTES, stream);
-  return launch_one<KS, BN, TD, MODE, STACK, false>(tm, tmo, a, C::SMEM_BYTES, stream);
+  if constexpr (BF16) {
+    return launch_one<KS, BN, TD, MODE, STACK, false, true>(tm, tmo, a, C::SMEM_BYTES, stream);
+  } else {
+    if (a.in_mr) return launch_one<KS, BN, TD, MODE, STACK, true>(tm, tmo, a, C::SMEM_BYTES, stream);
+    return launch_one<KS, BN, TD, MODE, STACK, false>(tm, tmo, a, C::SMEM_BYTES, stream);
+  }
 }
 
 int conv3d_k3_bn(int Cout) { return Cout == 64 ? 64 : 128; }
@@ -729,6 +764,70 @@ int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H
   return launch_cfg<3, 128, 2, 0>(x, a, Cin, stream);
 }
 
+// Data gradient of the k3 s1 p1 conv: dx = conv(dy, flipped / transposed filter) — the forward kernel with bf16
+// operands, bf16 output and no statistics.  `wpacked` comes from pack_weights_dgrad (Cout, Cin are the LAYER's).
+int conv3d_k3_dgrad(const void* dy, int NB, int D, int H, int W, int Cout, const void* wpacked, int Cin, void* dx,
+                    cudaStream_t stream) {
+  if (Cin % 64 || Cout % 64) return set_error("conv3d_k3_dgrad: Cin and Cout must be multiples of 64");
+  ConvTcArgs a{};
+  a.W = W, a.H = H, a.D = D, a.NB = NB;
+  a.chunks = Cout / 64;  // the GEMM's K runs over the layer's output channels
+  a.wpacked = static_cast<const uint8_t*>(wpacked);
+  a.out_raw = static_cast<__half*>(dx);  // 16-bit elements; written as bf16
+  a.ldo = Cin;
+  if (Cin == 64) {
+    a.n_tiles = 1;
+    return launch_cfg<3, 64, 4, 0, true, true>(dy, a, Cout, stream);
+  }
+  if (Cin % 128) return set_error("conv3d_k3_dgrad: Cin must be 64 or a multiple of 128");
+  a.n_tiles = Cin / 128;
+  return launch_cfg<3, 128, 2, 0, false, true>(dy, a, Cout, stream);
+}
+
+// Data gradient of ConvTranspose3d(k2, s2): with the output gradient gathered space-to-depth into
+// g[coarse voxel][tap * Cout + co] (space_to_depth_bf16), dx[v][ci] = sum_k g[v][k] * W[ci][k] is a 1x1x1 conv with
+// K = 8 * Cout and N = Cin: the same kernel, KS = 1, bf16.  `wpacked` from pack_weights_convT_dgrad.
+int conv3d_k1_bf16(const void* x, int NB, int D, int H, int W, int K, const void* wpacked, int N, void* y,
+                   cudaStream_t stream) {
+  if (K % 64 || N % 128) return set_error("conv3d_k1_bf16: K must be a multiple of 64 and N of 128");
+  ConvTcArgs a{};
+  a.W = W, a.H = H, a.D = D, a.NB = NB;
+  a.chunks = K / 64;
+  a.wpacked = static_cast<const uint8_t*>(wpacked);
+  a.out_raw = static_cast<__half*>(y);
+  a.ldo = N;
+  a.n_tiles = N / 128;
+  return launch_cfg<1, 128, 2, 0, false, true>(x, a, K, stream);
+}
+
+// w: IODHW fp32 (Cin, Cout, 2, 2, 2) of the transposed conv -> bf16 image [n_tile][chunk][row ci][64 k],
+// k = tap * Cout + co; 8 * Cout * Cin * 2 bytes.
+__global__ void pack_convT_dgrad_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cin, int Cout) {
+  const int K = 8 * Cout, chunks = K / 64;
+  const size_t total = static_cast<size_t>(Cin) * K;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kk = idx % 64;
+    size_t r0 = idx / 64;
+    const int r = r0 % 128;
+    r0 /= 128;
+    const int chunk = r0 % chunks;
+    const int n_tile = r0 / chunks;
+    const int ci = n_tile * 128 + r, k = chunk * 64 + kk;
+    const int tap = k / Cout, co = k - tap * Cout;
+    const __nv_bfloat16 b = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * Cout + co) * 8 + tap]);
+    const size_t stage = static_cast<size_t>(n_tile) * chunks + chunk;
+    out[stage * 128 * 64 + static_cast<size_t>(r) * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7))] =
+        *reinterpret_cast<const uint16_t*>(&b);
+  }
+}
+int pack_weights_convT_dgrad(const float* w, void* out, int Cin, int Cout, cudaStream_t stream) {
+  if (Cin % 128 || Cout % 8) return set_error("pack_weights_convT_dgrad: Cin must be a multiple of 128");
+  pack_convT_dgrad_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<uint16_t*>(out), Cin, Cout);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin,
                      const void* wpacked, const float* bias, int Cout, void* y, int y_ld, int y_coff,
                      cudaStream_t stream) {
@@ -757,8 +856,20 @@ int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int tra
   const int BN = transposed ? 128 : conv3d_k3_bn(Cout);
   const int ngemm = transposed ? 8 * Cout : Cout;
   if (ngemm % BN) return set_error("pack_weights: GEMM N not a multiple of the N tile");
-  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<__half*>(out), Cout, Cin, taps, BN,
-                                                         transposed, (!transposed && Cout == 64) ? 1 : 0);
+  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<uint16_t*>(out), Cout, Cin, taps, BN,
+                                                         transposed, (!transposed && Cout == 64) ? 1 : 0, 0);
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Packed bf16 image of the data-gradient filter of a k3 conv layer with weight w = OIDHW (Cout, Cin, 3, 3, 3);
+// same size as the forward image (packed_weight_bytes(Cout, Cin, 27, 0)).
+int pack_weights_dgrad(const float* w, void* out, int Cout, int Cin, cudaStream_t stream) {
+  if (Cin % 64 || Cout % 64) return set_error("pack_weights_dgrad: Cin and Cout must be multiples of 64");
+  const int BN = conv3d_k3_bn(Cin);  // GEMM N = the layer's Cin, GEMM K = the layer's Cout
+  if (Cin % BN) return set_error("pack_weights_dgrad: Cin must be 64 or a multiple of 128");
+  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<uint16_t*>(out), Cin, Cout, 27, BN, 0,
+                                                         Cin == 64 ? 1 : 0, 1);
   NC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -2,6 +2,7 @@
 // finalize/apply(+pool), the 1x1x1+sigmoid head, overlap blend, radix-select percentile, rescale/cast/crop and
 // the max-intensity projection.  All are coalesced, vectorised where the layout allows, and bit-exact where the
 // reference is integer / fixed-order fp32 arithmetic.  Reference citations are in include/neuroclear_b200.h.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "internal.h"
@@ -180,6 +181,21 @@ __device__ __forceinline__ void norm8(const __half* __restrict__ src, const floa
   }
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// BF16: the output (same values, relu(IN(raw))) is written as bf16 — the weight-gradient kernels read activations in
+// the gradient's format (tcgen05 cannot mix fp16 and bf16 operands).
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+  if constexpr (BF16)
+    return make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                      pack_bf16x2(o[6], o[7]));
+  return make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]));
+}
+
+template <bool BF16>
 __global__ void __launch_bounds__(256)
 in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, long long voxels, int C,
                      __half* __restrict__ y, int y_ld, int y_coff) {
@@ -198,12 +214,11 @@ in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ m
     }
     const long long gv = static_cast<long long>(nb) * voxels + vox;
     norm8(raw + gv * C + cg * 8, mu, rs, o);
-    uint4 pk = make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]),
-                          pack_f16x2(o[6], o[7]));
-    *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pk;
+    *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pack8<BF16>(o);
   }
 }
 
+template <bool BF16>
 __global__ void __launch_bounds__(256, 4)
 in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
                           int C, __half* __restrict__ y, int y_ld, int y_coff,
@@ -235,21 +250,18 @@ in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restric
       const long long gv = ((static_cast<long long>(nb) * D + dz) * H + hy) * W + wx;
       float o[8];
       norm8(raw + gv * C + cg * 8, mu, rs, o);
-      uint4 pk = make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]),
-                            pack_f16x2(o[6], o[7]));
-      *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pk;
+      *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pack8<BF16>(o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], o[i]);
     }
     const long long pv = ((static_cast<long long>(nb) * PD + pd) * PH + ph) * PW + pw;
-    uint4 pk = make_uint4(pack_f16x2(mx[0], mx[1]), pack_f16x2(mx[2], mx[3]), pack_f16x2(mx[4], mx[5]),
-                          pack_f16x2(mx[6], mx[7]));
-    *reinterpret_cast<uint4*>(pooled + pv * C + cg * 8) = pk;
+    *reinterpret_cast<uint4*>(pooled + pv * C + cg * 8) = pack8<BF16>(mx);
   }
 }
 
-int in_relu_apply(const void* raw_v, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
-                  int y_coff, void* pooled, cudaStream_t stream) {
+template <bool BF16>
+static int in_relu_apply_t(const void* raw_v, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y,
+                           int y_ld, int y_coff, void* pooled, cudaStream_t stream) {
   if (C % 8 || y_ld % 8 || y_coff % 8) return set_error("in_relu_apply: channel counts must be multiples of 8");
   if (NB > 65535) return set_error("in_relu_apply: NB too large");
   if (static_cast<long long>(D) * H * W * (C / 8) >= (1ll << 31)) return set_error("in_relu_apply: cube too large");
@@ -257,15 +269,24 @@ int in_relu_apply(const void* raw_v, const float* mean_rstd, int NB, int D, int 
   const int blocks = num_sms() * 8;
   if (pooled) {
     if ((D | H | W) & 1) return set_error("in_relu_apply: pooling needs even D, H, W");
-    in_relu_pool_apply_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, D, H, W, C,
+    in_relu_pool_apply_kernel<BF16><<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, D, H, W, C,
                                                                     static_cast<__half*>(y), y_ld, y_coff,
                                                                     static_cast<__half*>(pooled));
   } else {
-    in_relu_apply_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, static_cast<long long>(D) * H * W, C,
+    in_relu_apply_kernel<BF16><<<dim3(blocks, NB), 256, 0, stream>>>(raw, mean_rstd, static_cast<long long>(D) * H * W, C,
                                                                static_cast<__half*>(y), y_ld, y_coff);
   }
   NC_CUDA(cudaGetLastError());
   return 0;
+}
+
+int in_relu_apply(const void* raw_v, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
+                  int y_coff, void* pooled, cudaStream_t stream) {
+  return in_relu_apply_t<false>(raw_v, mean_rstd, NB, D, H, W, C, y, y_ld, y_coff, pooled, stream);
+}
+int in_relu_apply_bf16(const void* raw_v, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y,
+                       int y_ld, int y_coff, void* pooled, cudaStream_t stream) {
+  return in_relu_apply_t<true>(raw_v, mean_rstd, NB, D, H, W, C, y, y_ld, y_coff, pooled, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ head

@@ -39,6 +39,33 @@ int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H
 int convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin,
                      const void* wpacked, const float* bias, int Cout, void* y, int y_ld, int y_coff,
                      cudaStream_t stream);
+int conv3d_k3_dgrad(const void* dy, int NB, int D, int H, int W, int Cout, const void* wpacked, int Cin, void* dx,
+                    cudaStream_t stream);
+int pack_weights_dgrad(const float* w, void* out, int Cout, int Cin, cudaStream_t stream);
+int conv3d_k1_bf16(const void* x, int NB, int D, int H, int W, int K, const void* wpacked, int N, void* y,
+                   cudaStream_t stream);
+int pack_weights_convT_dgrad(const float* w, void* out, int Cin, int Cout, cudaStream_t stream);
+// unet_bwd.cu
+int bwd_blocks();
+int in_relu_bwd(const void* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, int mode,
+                const void* grad, int grad_ld, int grad_coff, const float* du, const float* w_head, const void* dpool,
+                float* scratch, float* m12, void* d_raw, cudaStream_t stream);
+int head_bwd(const void* raw, const float* mean_rstd, const float* hp, const float* dout, int NB, int D, int H, int W,
+             float* du, float* scratch, float* grads, cudaStream_t stream);
+int conv1_wgrad(const float* x, const void* dy, int NB, int D, int H, int W, float* scratch, float* dw,
+                cudaStream_t stream);
+int space_to_depth_bf16(const void* src, int ld, int coff, int NB, int D, int H, int W, int C, void* out,
+                        cudaStream_t stream);
+int colsum_bf16(const void* src, int ld, int coff, int NB, long long rows, int C, float* scratch, float* out,
+                cudaStream_t stream);
+int cast_f16_bf16(const void* src, int src_ld, int src_coff, long long rows, int C, void* dst, int dst_ld,
+                  int dst_coff, cudaStream_t stream);
+int in_relu_apply_bf16(const void* raw, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y, int y_ld,
+                       int y_coff, void* pooled, cudaStream_t stream);
+// wgrad3d_tc.cu
+size_t conv3d_wgrad_scratch_bytes(int ks, int NB, int D, int H, int W, int Cin, int Cout);
+int conv3d_wgrad(const void* x, int x_fmt, const void* dy, int dy_fmt, int NB, int D, int H, int W, int Cin,
+                 int Cout, int ks, void* scratch, float* dw, cudaStream_t stream);
 size_t packed_weight_bytes(int Cout, int Cin, int taps, int transposed);
 int pack_weights(const float* w, void* out, int Cout, int Cin, int taps, int transposed, cudaStream_t stream);
 

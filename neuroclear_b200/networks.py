@@ -87,8 +87,31 @@ class _ConvStack(nn.Module):
         self.convolution = nn.Sequential(*_conv_block(n_convs, cin, cout, norm_layer))
 
 
+class _UnetDeconvFn(torch.autograd.Function):
+    """Unet_deconv under autograd: forward / backward run on the training engine (neuroclear_b200.unet_train);
+    PyTorch only carries the tape.  The input receives no gradient (G_A's input is the data crop)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module.train_engine()
+        with torch.cuda.device(x.device):
+            y = eng.forward(x.detach().to(torch.float32)[:, 0].contiguous())
+        ctx.module, ctx.eng, ctx.saved = module, eng, eng.saved
+        eng.saved = None
+        return y[:, None]
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.eng
+        eng.saved, ctx.saved = ctx.saved, None
+        with torch.cuda.device(dy.device):
+            grads = eng.backward(dy[:, 0].contiguous())
+        return (None, None) + tuple(grads[k] for k, _ in ctx.module.named_parameters())
+
+
 class Unet_deconv(nn.Module):
-    """reference networks.py:478-538; forward on sm_100a kernels (inference only for now)."""
+    """reference networks.py:478-538 on sm_100a kernels: inference engine under no_grad / eval, training engine
+    (forward keeping activations + full backward) under autograd."""
 
     def __init__(self, input_nc, output_nc, norm_layer=None, dimension=3):
         super().__init__()
@@ -111,6 +134,8 @@ class Unet_deconv(nn.Module):
         self.one_by_one_2 = nn.Conv3d(output_nc, output_nc, 1, 1, 0)
         self._engine = None
         self._engine_sig = None
+        self._train_engine = None
+        self._train_sig = None
 
     # the packed fp16 weight cache follows the parameters: any in-place update, load_state_dict or device move
     # changes (data_ptr, _version) and triggers a repack on the next forward.
@@ -130,15 +155,30 @@ class Unet_deconv(nn.Module):
             self._engine_sig = sig
         return self._engine
 
+    def train_engine(self):
+        from .unet_train import UnetDeconvTrainEngine
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise NeuroclearError("Unet_deconv (B200): parameters are on the CPU; there is no CPU fallback — "
+                                  "move the network to a CUDA device")
+        sig = self._signature()
+        if self._train_engine is None or self._train_engine.device != p.device:
+            self._train_engine, self._train_sig = UnetDeconvTrainEngine(p.device), None
+        if self._train_sig != sig:
+            self._train_engine.load_state_dict(self.state_dict())
+            self._train_sig = sig
+        return self._train_engine
+
     def forward(self, inputs):
-        if torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in self.parameters())) \
-                and self.training:
-            raise NotImplementedError("autograd through the B200 unet_deconv path is not implemented yet; "
-                                      "call it under torch.no_grad() / model.eval()")
         if inputs.dim() != 5 or inputs.shape[1] != 1:
             raise NeuroclearError("Unet_deconv expects (N, 1, D, H, W)")
         if not inputs.is_cuda:
             raise NeuroclearError("Unet_deconv (B200): input is on the CPU; there is no CPU fallback")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if inputs.requires_grad:
+                raise NotImplementedError("the B200 unet_deconv path does not propagate a gradient to its input "
+                                          "(it is the first generator of the cycle, fed with data)")
+            return _UnetDeconvFn.apply(self, inputs, *self.parameters())
         eng = self.engine()
         with torch.cuda.device(inputs.device):
             x = inputs.detach().to(torch.float32)[:, 0].contiguous()

@@ -33,6 +33,9 @@ def _ref_dataset_and_assembler(vol, roi, ov, bc, normalize):
     return ds, asm, opt
 
 
+GRAD_SAMPLE_STRIDE = 61   # gradient tensors are committed as every 61st element
+
+
 def golden_geometry():
     """Geometry KATs from the reference classes themselves."""
     rows = []
@@ -118,6 +121,34 @@ def golden_unet():
     np.savez_compressed(os.path.join(GOLD, "unet_small.npz"), **out)
 
 
+def golden_unet_grad():
+    """Reference Unet_deconv under autograd (train mode, as train_onecube.py runs it): loss = sum(net(x) * dout) on
+    a 16x24x32 crop; records the output and every parameter gradient (sampled) and checks the oracle's gradients."""
+    rh.install()
+    from models import networks
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [], dimension=3)
+    net.train()
+    sd = unet.random_state_dict(seed=4, bias_std=0.1)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand((1, 1, 16, 24, 32), generator=g)
+    dout = torch.randn((1, 1, 16, 24, 32), generator=g) * 1e-3
+    y = net(x)
+    y.backward(dout)
+    y_or, g_or = unet.unet_deconv_gradients(x, sd, dout)
+    assert (y.detach() - y_or).abs().max().item() <= 1e-6
+    out = {"x": x.numpy(), "dout": dout.numpy(), "y": y.detach().numpy(),
+           "w_checksum": np.array(unet.state_dict_checksum(sd))}
+    for k, prm in net.named_parameters():
+        ref = prm.grad
+        scale = ref.abs().max().item()
+        assert (ref - g_or[k]).abs().max().item() <= 1e-4 * max(scale, 1e-7), k
+        out["gnorm_" + k] = np.array([float(ref.double().norm()), scale])
+        out["gsample_" + k] = ref.numpy().reshape(-1)[::GRAD_SAMPLE_STRIDE].copy()
+    np.savez_compressed(os.path.join(GOLD, "unet_grad.npz"), **out)
+
+
 def golden_mip():
     rh.install()
     from models.axial_to_lateral_gan_apollo_model import Volume
@@ -141,7 +172,6 @@ def golden_mip():
     np.savez_compressed(os.path.join(GOLD, "mip_12.npz"), **out)
 
 
-GRAD_SAMPLE_STRIDE = 61
 
 
 def golden_discriminator():
@@ -250,6 +280,7 @@ def main():
     golden_geometry()
     golden_dice_assemble()
     golden_unet()
+    golden_unet_grad()
     golden_mip()
     golden_discriminator()
     golden_apollo_discriminator_path()

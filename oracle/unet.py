@@ -45,37 +45,90 @@ def random_state_dict(seed: int = 0, bias_std: float = 0.0) -> dict:
     return sd
 
 
-def _conv_in_relu(x, sd, prefix):
-    x = F.conv3d(x, sd[prefix + ".weight"], sd[prefix + ".bias"], stride=1, padding=1)
+def _as_stored_fp16(t, on):
+    """Value rounded to fp16 with a straight-through gradient: what a tensor the B200 path keeps in fp16 looks like.
+    Only used to make gradient comparisons meaningful (see unet_deconv_gradients); never by the reference path."""
+    return t + (t.half().float() - t).detach() if on else t
+
+
+def _forced(t, stored, key):
+    """Replace the VALUE of t by stored[key] (straight-through gradient): differentiate at a given linearisation
+    point — the activations another implementation actually produced (see unet_deconv_gradients)."""
+    if stored is None or key not in stored:
+        return t
+    return t + (stored[key].to(t.dtype) - t).detach()
+
+
+def _conv_in_relu(x, sd, prefix, fp16_storage=False, stored=None, round_out=True):
+    x = F.conv3d(x, _as_stored_fp16(sd[prefix + ".weight"], fp16_storage), sd[prefix + ".bias"], stride=1, padding=1)
+    x = _forced(_as_stored_fp16(x, fp16_storage), stored, prefix)
     x = F.instance_norm(x, eps=1e-5)          # InstanceNorm3d(affine=False, track_running_stats=False)
-    return F.relu(x)
+    return _as_stored_fp16(F.relu(x), fp16_storage and round_out)
+
+
+def _pool(x, fp16_storage):
+    """MaxPool3d(2) (networks.py:491,494).  In storage mode x is the UNROUNDED activation: the B200 path pools the
+    fp32 values and rounds the maximum, so the arg-max (= where the gradient goes) is taken before rounding —
+    rounding first would create ties; the pooled VALUE is the same either way (rounding is monotonic)."""
+    return _as_stored_fp16(F.max_pool3d(x, 2), fp16_storage)
 
 
 def state_dict_checksum(sd: dict):
     return [float(sum(v.double().sum() for v in sd.values())), float(sum(v.double().abs().sum() for v in sd.values()))]
 
 
-def unet_deconv_forward(x: torch.Tensor, sd: dict, taps: dict | None = None) -> torch.Tensor:
-    """x: float32 (N,1,D,H,W) with D,H,W % 4 == 0 -> float32 (N,1,D,H,W) in (0,1).  networks.py:512-538."""
+def unet_deconv_forward(x: torch.Tensor, sd: dict, taps: dict | None = None, grad: bool = False,
+                        fp16_storage: bool = False, stored: dict | None = None) -> torch.Tensor:
+    """x: float32 (N,1,D,H,W) with D,H,W % 4 == 0 -> float32 (N,1,D,H,W) in (0,1).  networks.py:512-538.
+    grad=True records the autograd tape (unet_deconv_gradients); fp16_storage rounds every stored activation and
+    every tensor-core weight to fp16 like the B200 path does (gradient comparisons only)."""
+    def _conv_in_relu(x, sd, prefix, round_out=True):       # the module-level layer with the storage mode bound
+        return globals()["_conv_in_relu"](x, sd, prefix, fp16_storage, stored, round_out)
     def tap(name, t):
         if taps is not None:
             taps[name] = t
         return t
-    with torch.no_grad():
+    with torch.set_grad_enabled(grad):
         c1 = _conv_in_relu(x, sd, "double_conv1.convolution.0")
-        c1 = tap("conv1", _conv_in_relu(c1, sd, "double_conv1.convolution.3"))
-        p1 = F.max_pool3d(c1, 2)
+        c1 = _conv_in_relu(c1, sd, "double_conv1.convolution.3", round_out=False)
+        p1 = _pool(c1, fp16_storage)
+        c1 = tap("conv1", _as_stored_fp16(c1, fp16_storage))
         c2 = _conv_in_relu(p1, sd, "double_conv2.convolution.0")
-        c2 = tap("conv2", _conv_in_relu(c2, sd, "double_conv2.convolution.3"))
-        p2 = F.max_pool3d(c2, 2)
+        c2 = _conv_in_relu(c2, sd, "double_conv2.convolution.3", round_out=False)
+        p2 = _pool(c2, fp16_storage)
+        c2 = tap("conv2", _as_stored_fp16(c2, fp16_storage))
         b = _conv_in_relu(p2, sd, "bottom_layer.convolution.0")
         b = _conv_in_relu(b, sd, "bottom_layer.convolution.3")
         b = tap("bottom", _conv_in_relu(b, sd, "bottom_layer.convolution.6"))
-        t2 = tap("t_conv2", F.conv_transpose3d(b, sd["t_conv2.weight"], sd["t_conv2.bias"], stride=2))
+        t2 = tap("t_conv2", F.conv_transpose3d(b, _as_stored_fp16(sd["t_conv2.weight"], fp16_storage),
+                                               sd["t_conv2.bias"], stride=2))
+        t2 = _forced(_as_stored_fp16(t2, fp16_storage), stored, "t_conv2")
         e2 = _conv_in_relu(torch.cat([c2, t2], 1), sd, "ex_double_conv2.convolution.0")
         e2 = tap("ex_conv2", _conv_in_relu(e2, sd, "ex_double_conv2.convolution.3"))
-        t1 = F.conv_transpose3d(e2, sd["t_conv1.weight"], sd["t_conv1.bias"], stride=2)
+        t1 = _as_stored_fp16(F.conv_transpose3d(e2, _as_stored_fp16(sd["t_conv1.weight"], fp16_storage),
+                                                sd["t_conv1.bias"], stride=2), fp16_storage)
+        t1 = _forced(t1, stored, "t_conv1")
         e1 = tap("ex_conv1", _conv_in_relu(torch.cat([c1, t1], 1), sd, "ex_conv1_1.convolution.0"))
         o = F.conv3d(e1, sd["one_by_one.weight"], sd["one_by_one.bias"])
         o = F.conv3d(o, sd["one_by_one_2.weight"], sd["one_by_one_2.bias"])
         return torch.sigmoid(o)
+
+
+def unet_deconv_gradients(x: torch.Tensor, sd: dict, dout: torch.Tensor, fp16_storage: bool = False,
+                          stored: dict | None = None):
+    """Output and the gradient of sum(output * dout) w.r.t. every state_dict tensor — what autograd gives the
+    reference module when backward_G (axial_to_lateral_gan_apollo_model.py:255-283) hands it dL/d fake = dout.
+
+    fp16_storage: the gradient of a ReLU network is discontinuous in its activations — rounding a conv output to
+    fp16 (or computing it in TF32, as the reference does on a GPU) flips the ReLU mask of the ~1e-4 of the elements
+    that sit within rounding distance of zero, and every flip moves one gradient element by its full value: a
+    relative L2 change of sqrt(flipped fraction) ~ 1-2 % PER LAYER, 7-8 % at the first layer of this network
+    (measured with this very function).  Emulating the rounding is not enough either: two fp16 pipelines that
+    differ in the last bit of an fp32 accumulation drift apart by about one fp16 ulp within a few layers, which
+    flips a different set of masks.  To check the backward KERNELS tightly, the tests therefore differentiate at
+    the GPU's own linearisation point: `stored` maps a conv layer's state_dict prefix (and "t_conv1"/"t_conv2") to
+    the raw output the GPU forward actually stored; its value replaces the oracle's (straight-through gradient)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    y = unet_deconv_forward(x, leaves, grad=True, fp16_storage=fp16_storage, stored=stored)
+    y.backward(dout)
+    return y.detach(), {k: v.grad for k, v in leaves.items()}

@@ -1,0 +1,320 @@
+"""Training path of Unet_deconv on the GPU (forward keeping activations + full backward) against
+ (a) the fixture recorded from the REFERENCE module under autograd (tests/golden/unet_grad.npz, oracle/make_golden.py),
+ (b) the oracle's autograd on other shapes, and (c) torch CPU autograd for every backward kernel on its own.
+Gradients travel in bf16 (8 mantissa bits), so tensors are compared in relative L2 norm and max-abs relative to
+the tensor's max; biases in front of InstanceNorm(affine=False) have a mathematically zero gradient.
+
+Tolerances.  The gradient of a ReLU network is discontinuous in its activations: rounding conv outputs to fp16 (as
+this path stores them; TF32 on the reference's own GPU path does the same) flips the ReLU mask of the ~1e-3 of the
+elements next to zero and each flip moves a gradient element by its full value — 2-4 % relative L2 per layer, 8-10 %
+at the first layer, reproduced on the CPU oracle alone (oracle/unet.py::unet_deconv_gradients).  Hence:
+  * the check of the backward KERNELS differentiates the oracle at the GPU's own linearisation point (the raw conv
+    outputs the GPU forward stored are forced into the oracle's forward): 3e-2, the bf16 gradient noise;
+  * against the pure-fp32 reference fixture: 0.15 — the reference-pinned end-to-end check."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+STRIDE = 61
+NOISE_ONLY = ("double_conv1.convolution", "double_conv2.convolution", "bottom_layer.convolution",
+              "ex_double_conv2.convolution", "ex_conv1_1.convolution")
+
+
+def _lib():
+    from neuroclear_b200 import _lib
+    return _lib
+
+
+def ndhwc(t, dtype):
+    """(N,C,D,H,W) float -> contiguous (N,D,H,W,C) of dtype on the GPU"""
+    return t.permute(0, 2, 3, 4, 1).contiguous().to("cuda", dtype)
+
+
+def ncdhw(t):
+    return t.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / max(float(b.double().norm()), 1e-30))
+
+
+def grad_err(got, ref):
+    got, ref = got.detach().float().cpu().reshape(-1), ref.detach().float().cpu().reshape(-1)
+    assert torch.isfinite(got).all()
+    return rel_l2(got, ref), float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
+
+
+def check_grad(name, got, ref, rel=2e-2, mx=5e-2):
+    r, m = grad_err(got, ref)
+    assert r <= rel and m <= mx, "%s: rel L2 %.3g, max-abs/max %.3g" % (name, r, m)
+    return r
+
+
+def check_all(pairs, rel, mx):
+    """pairs: [(name, got, ref)] — report every tensor before failing, so one GPU run shows the whole picture"""
+    bad = []
+    for name, got, ref in pairs:
+        r, m = grad_err(got, ref)
+        print("  %-42s rel L2 %.4f  max-abs/max %.4f" % (name, r, m))
+        if not (r <= rel and m <= mx):
+            bad.append((name, r, m))
+    assert not bad, bad
+
+
+# --------------------------------------------------------------------------------------------- whole network
+def _engine(sd):
+    from neuroclear_b200.unet_train import UnetDeconvTrainEngine
+    eng = UnetDeconvTrainEngine("cuda")
+    eng.load_state_dict(sd)
+    return eng
+
+
+def _stored(saved):
+    """the GPU forward's stored raw conv outputs / transposed-conv outputs as NCDHW float32 CPU tensors"""
+    nb, dims = saved["nb"], saved["dims"]
+    out = {}
+    for name, t in saved["raw"].items():
+        lvl = 0 if t.numel() == nb * saved["vox"][0] * 64 else (1 if t.numel() == nb * saved["vox"][1] * 128 else 2)
+        out[name] = ncdhw(t.view(nb, *dims[lvl], -1))
+    out["t_conv1"] = ncdhw(saved["cat1"].view(nb, *dims[0], 128)[..., 64:])
+    out["t_conv2"] = ncdhw(saved["cat2"].view(nb, *dims[1], 256)[..., 128:])
+    return out
+
+
+def test_gradients_match_reference_fixture():
+    from oracle import unet
+    z = np.load(os.path.join(GOLD, "unet_grad.npz"))
+    sd = unet.random_state_dict(seed=4, bias_std=0.1)
+    np.testing.assert_allclose(np.array(unet.state_dict_checksum(sd)), z["w_checksum"], rtol=1e-9)
+    eng = _engine(sd)
+    x = torch.from_numpy(z["x"]).cuda()[:, 0].contiguous()
+    y = eng.forward(x)
+    assert float((y.cpu() - torch.from_numpy(z["y"])[:, 0]).abs().max()) <= 5e-3
+    stored = _stored(eng.saved)
+    grads = eng.backward(torch.from_numpy(z["dout"]).cuda()[:, 0].contiguous())
+    assert set(grads) == set(unet.STATE_DICT_SHAPES)
+    pairs = []
+    for k, shape in unet.STATE_DICT_SHAPES.items():
+        g = grads[k]
+        assert tuple(g.shape) == shape, k
+        ref = torch.from_numpy(z["gsample_" + k])
+        got = g.float().cpu().reshape(-1)[::STRIDE]
+        if k.endswith(".bias") and k.startswith(NOISE_ONLY):
+            assert float(got.abs().max()) <= 1e-6, k     # reference: rounding noise ~1e-8 around an exact zero
+            continue
+        pairs.append((k, got, ref))
+    print("\nvs the REFERENCE fixture (pure fp32 forward):")
+    check_all(pairs, rel=0.15, mx=0.3)
+    # the same gradients against the oracle differentiated at the GPU's own linearisation point
+    _, g_or = unet.unet_deconv_gradients(torch.from_numpy(z["x"]), sd, torch.from_numpy(z["dout"]), fp16_storage=True,
+                                         stored=stored)
+    print("vs the oracle at the GPU's linearisation point:")
+    check_all([(k, grads[k], g_or[k]) for k, _, _ in pairs], rel=3e-2, mx=8e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 16), (1, 8, 40, 20)])
+def test_gradients_match_oracle(shape):
+    from oracle import unet
+    sd = unet.random_state_dict(seed=11, bias_std=0.05)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((shape[0], 1) + shape[1:], generator=g)
+    dout = torch.randn(x.shape, generator=g) * 1e-4           # magnitudes like d(mean L1)/d voxel: fp16 would underflow
+    eng = _engine(sd)
+    y = eng.forward(x.cuda()[:, 0].contiguous())
+    stored = _stored(eng.saved)
+    y_ref, g_ref = unet.unet_deconv_gradients(x, sd, dout, fp16_storage=True, stored=stored)
+    assert float((y.cpu() - y_ref[:, 0]).abs().max()) <= 5e-3
+    grads = eng.backward(dout.cuda()[:, 0].contiguous())
+    pairs = []
+    for k in unet.STATE_DICT_SHAPES:
+        if k.endswith(".bias") and k.startswith(NOISE_ONLY):
+            assert float(grads[k].abs().max()) <= 1e-6
+            continue
+        pairs.append((k, grads[k], g_ref[k]))
+    print()
+    check_all(pairs, rel=3e-2, mx=8e-2)
+
+
+def test_module_autograd_and_adam_step():
+    """networks.define_G('unet_deconv') in train mode: loss.backward() fills .grad of every parameter and an
+    optimizer step changes the next forward (packed-weight cache invalidation)."""
+    from neuroclear_b200 import networks
+    from oracle import unet
+    sd = unet.random_state_dict(seed=3, bias_std=0.05)
+    net = networks.define_G(1, 1, 64, "unet_deconv", "instance", False, "kaiming", 0.02, [0], dimension=3)
+    mod = net.module if hasattr(net, "module") else net
+    mod.load_state_dict(sd)
+    net.train()
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand((1, 1, 16, 16, 16), generator=g)
+    target = torch.rand(x.shape, generator=g)
+    y = net(x.cuda())
+    assert y.requires_grad
+    loss = (y - target.cuda()).abs().mean()
+    loss.backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    y_ref = unet.unet_deconv_forward(x, leaves, grad=True)
+    (y_ref - target).abs().mean().backward()
+    pairs = []
+    for k, p in mod.named_parameters():
+        assert p.grad is not None and tuple(p.grad.shape) == tuple(p.shape), k
+        if k.endswith(".bias") and k.startswith(NOISE_ONLY):
+            continue
+        pairs.append((k, p.grad, leaves[k].grad))
+    print()
+    check_all(pairs, rel=0.2, mx=0.5)       # plain fp32 oracle: ReLU-mask flips (module docstring) + sign(y - t) flips
+    opt = torch.optim.Adam(mod.parameters(), lr=1e-3)
+    opt.step()
+    with torch.no_grad():
+        y2 = net(x.cuda())
+    assert float((y2 - y.detach()).abs().max()) > 1e-4
+
+
+# --------------------------------------------------------------------------------------------- single kernels
+def _mean_rstd(raw_f32):
+    """(N,C,D,H,W) -> float32 (N,2,C) on the GPU, InstanceNorm3d statistics (biased variance, eps 1e-5)"""
+    mean = raw_f32.mean(dim=(2, 3, 4))
+    var = raw_f32.var(dim=(2, 3, 4), unbiased=False)
+    return torch.stack([mean, 1.0 / torch.sqrt(var + 1e-5)], 1).contiguous().cuda()
+
+
+@pytest.mark.parametrize("mode,c", [(0, 64), (0, 256), (1, 64), (2, 64), (2, 128)])
+def test_in_relu_bwd(mode, c):
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(20 + mode + c)
+    nb, d, h, w = 2, 6, 8, 10
+    raw = (torch.randn((nb, c, d, h, w), generator=g) * 1.5 + 0.3).half().float()
+    raw_leaf = raw.clone().requires_grad_(True)
+    act = F.relu(F.instance_norm(raw_leaf, eps=1e-5))
+    kw = dict(grad=None, ld=0, coff=0, du=None, wh=None, dpool=None)
+    if mode == 0:
+        ld, coff = c + 64, 32                                              # a slice of a wider gradient tensor
+        dA = (torch.randn((nb, ld, d, h, w), generator=g) * 1e-4).bfloat16().float()
+        act.backward(dA[:, coff:coff + c])
+        kw.update(grad=ndhwc(dA, torch.bfloat16), ld=ld, coff=coff)
+    elif mode == 1:
+        du = torch.randn((nb, 1, d, h, w), generator=g) * 1e-3
+        wh = torch.randn(64, generator=g)
+        act.backward(du * wh.view(1, 64, 1, 1, 1))
+        kw.update(du=du.cuda().contiguous(), wh=wh.cuda())
+    else:
+        skip = (torch.randn((nb, 2 * c, d, h, w), generator=g) * 1e-4).bfloat16().float()
+        dp = (torch.randn((nb, c, d // 2, h // 2, w // 2), generator=g) * 1e-4).bfloat16().float()
+        ((act * skip[:, :c]).sum() + (F.max_pool3d(act, 2) * dp).sum()).backward()
+        kw.update(grad=ndhwc(skip, torch.bfloat16), ld=2 * c, coff=0, dpool=ndhwc(dp, torch.bfloat16))
+    raw_dev = ndhwc(raw, torch.float16)
+    mr = _mean_rstd(raw)
+    scratch = torch.empty(lib.nc_bwd_scratch_bytes(nb) // 4, dtype=torch.float32, device="cuda")
+    m12 = torch.empty(nb * 2 * c, dtype=torch.float32, device="cuda")
+    d_raw = torch.empty((nb, d, h, w, c), dtype=torch.bfloat16, device="cuda")
+    L.call("nc_in_relu_bwd", L.ptr(raw_dev), L.ptr(mr), nb, d, h, w, c, mode, L.ptr(kw["grad"]), kw["ld"], kw["coff"],
+           L.ptr(kw["du"]), L.ptr(kw["wh"]), L.ptr(kw["dpool"]), L.ptr(scratch), L.ptr(m12), L.ptr(d_raw),
+           L.stream_ptr())
+    torch.cuda.synchronize()
+    check_grad("d_raw mode %d" % mode, ncdhw(d_raw), raw_leaf.grad, rel=1e-2, mx=2e-2)
+
+
+def test_head_bwd():
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(31)
+    nb, d, h, w = 2, 6, 10, 9
+    raw = (torch.randn((nb, 64, d, h, w), generator=g) + 0.2).half().float()
+    hp = torch.cat([torch.randn(64, generator=g) * 0.3, torch.tensor([0.1, 0.8, -0.2])])
+    prm = hp.clone().requires_grad_(True)
+    act = F.relu(F.instance_norm(raw, eps=1e-5))
+    u1 = (act * prm[:64].view(1, 64, 1, 1, 1)).sum(1, keepdim=True) + prm[64]
+    u1.retain_grad()
+    out = torch.sigmoid(prm[65] * u1 + prm[66])
+    dout = torch.randn(out.shape, generator=g) * 1e-3
+    out.backward(dout)
+    raw_dev, mr = ndhwc(raw, torch.float16), _mean_rstd(raw)
+    scratch = torch.empty(lib.nc_bwd_scratch_bytes(nb) // 4, dtype=torch.float32, device="cuda")
+    du = torch.empty((nb, d, h, w), dtype=torch.float32, device="cuda")
+    grads = torch.empty(68, dtype=torch.float32, device="cuda")
+    hp_dev, dout_dev = hp.cuda(), dout[:, 0].contiguous().cuda()
+    L.call("nc_head_1x1_sigmoid_bwd", L.ptr(raw_dev), L.ptr(mr), L.ptr(hp_dev), L.ptr(dout_dev), nb, d, h, w,
+           L.ptr(du), L.ptr(scratch), L.ptr(grads), L.stream_ptr())
+    torch.cuda.synchronize()
+    check_grad("du", du.cpu(), u1.grad[:, 0], rel=2e-3, mx=2e-3)
+    check_grad("head grads", grads[:67].cpu(), prm.grad, rel=2e-3, mx=2e-3)
+
+
+def test_first_layer_wgrad():
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(32)
+    nb, d, h, w = 2, 7, 9, 12
+    x = torch.rand((nb, 1, d, h, w), generator=g)
+    dy = (torch.randn((nb, 64, d, h, w), generator=g) * 1e-3).bfloat16().float()
+    wt = torch.zeros((64, 1, 3, 3, 3), requires_grad=True)
+    F.conv3d(x, wt, padding=1).backward(dy)
+    scratch = torch.empty(lib.nc_bwd_scratch_bytes(nb) // 4, dtype=torch.float32, device="cuda")
+    dw = torch.empty((64, 27), dtype=torch.float32, device="cuda")
+    x_dev, dy_dev = x[:, 0].contiguous().cuda(), ndhwc(dy, torch.bfloat16)
+    L.call("nc_conv3d_cin1_k3_wgrad", L.ptr(x_dev), L.ptr(dy_dev), nb, d, h, w, L.ptr(scratch), L.ptr(dw),
+           L.stream_ptr())
+    torch.cuda.synchronize()
+    check_grad("dW first layer", dw.cpu(), wt.grad.reshape(64, 27), rel=1e-4, mx=1e-4)
+
+
+@pytest.mark.parametrize("cin,cout", [(128, 64), (256, 128)])
+def test_convT_backward(cin, cout):
+    """space-to-depth + k1 GEMM (data gradient) + ks=1 weight-gradient GEMM + column sums (bias)"""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(33)
+    nb, d, h, w = 1, 3, 9, 6
+    x = torch.randn((nb, cin, d, h, w), generator=g).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn((cin, cout, 2, 2, 2), generator=g) * 0.05).requires_grad_(True)
+    bias = torch.zeros(cout, requires_grad=True)
+    ld, coff = 2 * cout, cout                                              # the layer writes the upper concat half
+    dcat = (torch.randn((nb, ld, 2 * d, 2 * h, 2 * w), generator=g) * 1e-3).bfloat16().float()
+    F.conv_transpose3d(x, wt.bfloat16().float(), bias, stride=2).backward(dcat[:, coff:])
+    wt_grad = torch.autograd.grad(F.conv_transpose3d(x.detach(), wt, bias, stride=2), wt, dcat[:, coff:])[0]
+    s = L.stream_ptr()
+    dcat_dev, x_dev = ndhwc(dcat, torch.bfloat16), ndhwc(x.detach(), torch.bfloat16)
+    gbuf = torch.empty((nb, d, h, w, 8 * cout), dtype=torch.bfloat16, device="cuda")
+    L.call("nc_space_to_depth_bf16", L.ptr(dcat_dev), ld, coff, nb, d, h, w, cout, L.ptr(gbuf), s)
+    packed = torch.empty(8 * cout * cin * 2, dtype=torch.uint8, device="cuda")
+    w_dev = wt.detach().cuda().contiguous()
+    L.call("nc_pack_weights_convT3d_k2s2_dgrad", L.ptr(w_dev), cin, cout, L.ptr(packed), s)
+    dx = torch.empty((nb, d, h, w, cin), dtype=torch.bfloat16, device="cuda")
+    L.call("nc_conv3d_k1_bf16", L.ptr(gbuf), nb, d, h, w, 8 * cout, L.ptr(packed), cin, L.ptr(dx), s)
+    ws = torch.empty(lib.nc_conv3d_wgrad_scratch_bytes(1, nb, d, h, w, cin, 8 * cout), dtype=torch.uint8, device="cuda")
+    dw = torch.empty(8 * cout * cin, dtype=torch.float32, device="cuda")
+    L.call("nc_conv3d_wgrad", L.ptr(x_dev), 1, L.ptr(gbuf), 1, nb, d, h, w, cin, 8 * cout, 1, L.ptr(ws), L.ptr(dw), s)
+    scratch = torch.empty(lib.nc_bwd_scratch_bytes(nb) // 4, dtype=torch.float32, device="cuda")
+    db = torch.empty(cout, dtype=torch.float32, device="cuda")
+    L.call("nc_colsum_bf16", L.ptr(dcat_dev), ld, coff, nb, L.i64(8 * d * h * w), cout, L.ptr(scratch), L.ptr(db), s)
+    torch.cuda.synchronize()
+    check_grad("convT dx", ncdhw(dx), x.grad, rel=1e-2, mx=2e-2)
+    check_grad("convT dW", dw.view(8, cout, cin).permute(2, 1, 0).reshape(cin, cout, 2, 2, 2).cpu(), wt_grad,
+               rel=1e-4, mx=1e-4)
+    check_grad("convT db", db.cpu(), bias.grad, rel=1e-5, mx=1e-5)
+
+
+def test_apply_bf16_and_cast():
+    L = _lib()
+    g = torch.Generator().manual_seed(34)
+    nb, d, h, w, c = 1, 4, 6, 8, 64
+    raw = torch.randn((nb, c, d, h, w), generator=g).half().float()
+    raw_dev, mr = ndhwc(raw, torch.float16), _mean_rstd(raw)
+    y = torch.zeros((nb, d, h, w, 2 * c), dtype=torch.bfloat16, device="cuda")
+    pooled = torch.empty((nb, d // 2, h // 2, w // 2, c), dtype=torch.bfloat16, device="cuda")
+    L.call("nc_in_relu_apply_bf16", L.ptr(raw_dev), L.ptr(mr), nb, d, h, w, c, L.ptr(y), 2 * c, 0, L.ptr(pooled),
+           L.stream_ptr())
+    src = torch.randn((nb, d, h, w, 2 * c), generator=g).half().cuda()
+    L.call("nc_cast_f16_bf16", L.ptr(src), 2 * c, c, L.i64(nb * d * h * w), c, L.ptr(y), 2 * c, c, L.stream_ptr())
+    torch.cuda.synchronize()
+    act = F.relu(F.instance_norm(raw, eps=1e-5))
+    assert float((ncdhw(y[..., :c]) - act).abs().max()) <= 2e-2            # bf16 rounding of values up to ~4
+    assert float((ncdhw(pooled) - F.max_pool3d(act, 2)).abs().max()) <= 2e-2
+    assert torch.equal(y[..., c:].float(), src[..., c:].float().bfloat16().float())
