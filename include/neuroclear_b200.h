@@ -104,6 +104,7 @@ int nc_conv3d_k3_fwd(const void* x_f16, const float* in_mean_rstd, int32_t nb, i
  *   is the voxel (both operands read MN-major from TMA-staged halo planes), split-K over the CTAs with a fixed-order
  *   (deterministic) reduction.  x: 16-bit NDHWC (NB,D,H,W,Cin), x_fmt 0 = fp16 / 1 = bf16 (the forward activations
  *   are fp16); dy likewise (dy_fmt).  ks in {3,5} (Unet_deconv k3; DeepLinearGenerator k5 / k3, networks.py:899-905).
+ *   ks = 71 selects the 7 x 1 x 1 (depth-only) filter of the im2col'ed k7 layer, ks = 1 the 1x1x1 GEMM.
  *   scratch: nc_conv3d_wgrad_scratch_bytes(...) bytes; dw: float32 OIDHW (Cout,Cin,ks,ks,ks), overwritten. */
 int nc_pack_weights_conv3d_k3_dgrad(const float* w_oidhw, int32_t cout, int32_t cin, void* packed,
                                     nc_stream_t stream);
@@ -158,8 +159,28 @@ int nc_head_1x1_sigmoid_bwd(const void* raw_f16, const float* mean_rstd, const f
                             nc_stream_t stream);
 /* Weight gradient of the Cin = 1 first conv (networks.py:420): dw float32 (64, 27). x float32 (NB,D,H,W),
  * dy bf16 (NB,D,H,W,64). */
-int nc_conv3d_cin1_k3_wgrad(const float* x, const void* dy_bf16, int32_t nb, int32_t d, int32_t h, int32_t w,
-                            void* scratch, float* dw, nc_stream_t stream);
+int nc_conv3d_cin1_k3_wgrad(const float* x, const void* dy, int32_t dy_fmt /* 0 fp16, 1 bf16 */, int32_t nb,
+                            int32_t d, int32_t h, int32_t w, void* scratch, float* dw, nc_stream_t stream);
+
+/* ---- DeepLinearGenerator (networks.py:893-917; G_B of axial_to_lateral_gan_apollo): k7 1->64, k5 64->64, k3 64->64,
+ * three 1x1 (64->32->16->1), no bias, no activation.
+ *   k7 layer  = nc_im2col49 (the 7x7 in-plane neighbourhood as 49 (+15 zero) channels) + nc_conv3d_tc_64(ksd 7, ksp 1);
+ *               backward: nc_conv3d_wgrad(ks = 71), nc_conv3d_tc_64(fmt 1, flipped filter) + nc_col2im49.
+ *   k5 layer  = nc_conv3d_tc_64(ksd 5, ksp 5); backward: nc_conv3d_wgrad(ks = 5), nc_conv3d_tc_64(fmt 1).
+ *   k3 + 1x1s = folded exactly into ONE 64->1 k3 stencil K[ci][tap] = sum_co (W6 W5 W4)[co] W3[co][ci][tap]:
+ *               nc_stencil64to1_fwd; backward: nc_stencil64to1_bwd_data (dh, bf16) and, for dK,
+ *               nc_conv3d_cin1_k3_wgrad(x = dout, dy = h) with the taps reversed.
+ * nc_pack_weights_64: w float32 (64, 64, taps) -> packed image (fp16; dgrad != 0: channel-transposed, taps reversed,
+ * bf16), 64*64*taps*2 bytes.  nc_conv3d_tc_64: x, y 16-bit NDHWC (NB,D,H,W,64); fmt 0 = fp16, 1 = bf16. */
+int nc_im2col49(const float* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t fmt, void* out, nc_stream_t stream);
+int nc_col2im49(const void* g_bf16, int32_t nb, int32_t d, int32_t h, int32_t w, float* dx, nc_stream_t stream);
+int nc_pack_weights_64(const float* w, int32_t taps, int32_t dgrad, void* packed, nc_stream_t stream);
+int nc_conv3d_tc_64(const void* x, int32_t fmt, int32_t nb, int32_t d, int32_t h, int32_t w, const void* packed,
+                    int32_t ksd, int32_t ksp, void* y, nc_stream_t stream);
+int nc_stencil64to1_fwd(const void* h_f16, const float* k, int32_t nb, int32_t d, int32_t h, int32_t w, float* out,
+                        nc_stream_t stream);
+int nc_stencil64to1_bwd_data(const float* dout, const float* k, int32_t nb, int32_t d, int32_t h, int32_t w,
+                             void* dh_bf16, nc_stream_t stream);
 
 /* nn.ConvTranspose3d(Cin -> Cout, k2 s2) t_conv2 / t_conv1 (networks.py:500,503) fused with the channel concat
  * torch.cat([skip, up], 1) (networks.py:526,531): GEMM + pixel-shuffle scatter + bias, written as fp16 into

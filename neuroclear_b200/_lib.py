@@ -44,7 +44,13 @@ SIGNATURES = {
     "nc_in_relu_apply_bf16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
     "nc_in_relu_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "nc_head_1x1_sigmoid_bwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
-    "nc_conv3d_cin1_k3_wgrad": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "nc_conv3d_cin1_k3_wgrad": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "nc_im2col49": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "nc_col2im49": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
+    "nc_pack_weights_64": (C.c_int, [vp, i32, i32, vp, vp]),
+    "nc_conv3d_tc_64": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "nc_stencil64to1_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+    "nc_stencil64to1_bwd_data": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
     "nc_convT3d_k2s2_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
     "nc_in_stats_scratch_bytes": (i64, [i32, i32]),
     "nc_in_stats_finalize": (C.c_int, [vp, i32, i64, i32, i64, f32, vp, vp, vp]),

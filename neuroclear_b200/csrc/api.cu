@@ -118,9 +118,31 @@ int nc_head_1x1_sigmoid_bwd(const void* raw, const float* mean_rstd, const float
                             nc_stream_t stream) {
   return head_bwd(raw, mean_rstd, hp, dout, nb, d, h, w, du, static_cast<float*>(scratch), grads, S(stream));
 }
-int nc_conv3d_cin1_k3_wgrad(const float* x, const void* dy, int32_t nb, int32_t d, int32_t h, int32_t w,
-                            void* scratch, float* dw, nc_stream_t stream) {
-  return conv1_wgrad(x, dy, nb, d, h, w, static_cast<float*>(scratch), dw, S(stream));
+int nc_conv3d_cin1_k3_wgrad(const float* x, const void* dy, int32_t dy_fmt, int32_t nb, int32_t d, int32_t h,
+                            int32_t w, void* scratch, float* dw, nc_stream_t stream) {
+  return conv1_wgrad(x, dy, dy_fmt, nb, d, h, w, static_cast<float*>(scratch), dw, S(stream));
+}
+int nc_im2col49(const float* x, int32_t nb, int32_t d, int32_t h, int32_t w, int32_t fmt, void* out,
+                nc_stream_t stream) {
+  return im2col49(x, nb, d, h, w, fmt, out, S(stream));
+}
+int nc_col2im49(const void* g, int32_t nb, int32_t d, int32_t h, int32_t w, float* dx, nc_stream_t stream) {
+  return col2im49(g, nb, d, h, w, dx, S(stream));
+}
+int nc_stencil64to1_fwd(const void* hin, const float* k, int32_t nb, int32_t d, int32_t h, int32_t w, float* out,
+                        nc_stream_t stream) {
+  return stencil64to1_fwd(hin, k, nb, d, h, w, out, S(stream));
+}
+int nc_stencil64to1_bwd_data(const float* dout, const float* k, int32_t nb, int32_t d, int32_t h, int32_t w, void* dh,
+                             nc_stream_t stream) {
+  return stencil64to1_bwd_data(dout, k, nb, d, h, w, dh, S(stream));
+}
+int nc_conv3d_tc_64(const void* x, int32_t fmt, int32_t nb, int32_t d, int32_t h, int32_t w, const void* packed,
+                    int32_t ksd, int32_t ksp, void* y, nc_stream_t stream) {
+  return conv3d_tc_64(x, fmt, nb, d, h, w, packed, ksd, ksp, y, S(stream));
+}
+int nc_pack_weights_64(const float* w, int32_t taps, int32_t dgrad, void* packed, nc_stream_t stream) {
+  return pack_weights_64(w, packed, taps, dgrad, S(stream));
 }
 int nc_space_to_depth_bf16(const void* src, int32_t ld, int32_t coff, int32_t nb, int32_t d, int32_t h, int32_t w,
                            int32_t c, void* out, nc_stream_t stream) {

@@ -40,19 +40,24 @@ constexpr int pow2_at_least(int v) { return v <= 32 ? 32 : v <= 64 ? 64 : v <= 1
 // the kernel off the shared-memory-bandwidth roof an N = 64 MMA sits on (4 KB of A per 32 math cycles).  A tile is
 // TD = 4 output planes processed in two phases of three input planes; each phase walks all nine (kh,kw) weight
 // stages (192 rows = [kd2 | kd1 | kd0]), so the 6-slot plane ring always prefetches the next phase's planes.
-template <int KS, int BN, int TD, bool STACK = false, bool OUT_STAGE = false>
+// KS = in-plane (h, w) filter extent, KSD = extent along d (= KS for the cubic filters of Unet_deconv; the k7 Cin = 1
+// layer of DeepLinearGenerator runs as KS = 1, KSD = 7 over a 49-channel in-plane im2col of its input).
+template <int KS, int BN, int TD, bool STACK = false, bool OUT_STAGE = false, int KSD = KS>
 struct ConvCfg {
   static constexpr int PAD = KS / 2;
+  static constexpr int PAD_D = KSD / 2;
   static constexpr int HALO_W = TW + KS - 1;
   static constexpr int HALO_H = TH + KS - 1;
   static constexpr int PLANE_ROWS = HALO_W * HALO_H;
   static constexpr int PLANE_BOX_BYTES = PLANE_ROWS * 128;
   static constexpr int PLANE_BYTES = (PLANE_BOX_BYTES + 1023) / 1024 * 1024;
-  static constexpr int PPC = TD + KS - 1;  // halo planes per (tile, chunk)
-  static constexpr int NSLOT = STACK ? PPC : PPC + 2;  // plane ring depth (two planes / one phase of look-ahead)
-  static constexpr int TAPS = KS * KS * KS;
+  static constexpr int PPC = TD + KSD - 1;  // halo planes per (tile, chunk)
+  // plane ring depth: two planes (STACK: one phase) of look-ahead; the 30 KB planes of k5 leave room for none —
+  // there the ring refills as the kd groups retire their planes
+  static constexpr int NSLOT = (STACK || KS >= 5) ? PPC : PPC + 2;
+  static constexpr int TAPS = KSD * KS * KS;
   static constexpr int BSTAGE_BYTES = (STACK ? 3 * BN : BN) * 128;
-  static constexpr int STAGES_PER_CHUNK = STACK ? 2 * KS * KS : KS * KS * KS;
+  static constexpr int STAGES_PER_CHUNK = STACK ? 2 * KS * KS : TAPS;
   static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4;  // barriers + per-warp stats scratch
   static constexpr int SMEM_LIMIT = 232448;
   static constexpr int OUT_BYTES = OUT_STAGE ? 2 * 128 * 128 : 0;  // two 128-row x 64-channel fp16 store tiles
@@ -64,7 +69,8 @@ struct ConvCfg {
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(NBST >= 2, "weight ring too shallow");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "bad BN");
-  static_assert(!STACK || (KS == 3 && BN == 64 && TD == 4), "STACK is built for k3, Cout 64, four output planes");
+  static_assert(!STACK || (KS == 3 && KSD == 3 && BN == 64 && TD == 4),
+                "STACK is built for k3, Cout 64, four output planes");
 };
 
 struct ConvTcArgs {
@@ -151,11 +157,11 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // read-raw / write-normalised pass between two convolutions.
 // BF16: operands and output are bf16 and no statistics are taken — the data-gradient pass of the same convolution
 // (gradients need bf16's exponent range; see conv3d_k3_dgrad).
-template <int KS, int BN, int TD, int MODE, bool STACK, bool XF, bool BF16 = false>
+template <int KS, int BN, int TD, int MODE, bool STACK, bool XF, bool BF16 = false, int KSD = KS>
 __global__ void __launch_bounds__(XF ? 384 : 256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapOut,
                  const ConvTcArgs args) {
-  using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
+  using C = ConvCfg<KS, BN, TD, STACK, MODE == 1, KSD>;
   // __align__(1024), not a hand-rounded pointer: an integer round trip makes the compiler forget the address space
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smA = smem;
@@ -217,7 +223,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             ptx::mbar_wait(&planeEmpty[slot], ph ^ 1);
             ptx::mbar_arrive_expect_tx(&planeFull[slot], C::PLANE_BOX_BYTES);
             ptx::tma_load_5d(smA + slot * C::PLANE_BYTES, &tmapA, &planeFull[slot], c * 64, t.w0 - C::PAD,
-                             t.h0 - C::PAD, t.d0 - C::PAD + i, t.nb);
+                             t.h0 - C::PAD, t.d0 - C::PAD_D + i, t.nb);
             if (++slot == C::NSLOT) {
               slot = 0;
               ph ^= 1;
@@ -351,7 +357,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
           }
         } else {
           int waited = 0;
-          for (int kd = 0; kd < KS; ++kd) {
+          for (int kd = 0; kd < KSD; ++kd) {
             for (; waited <= TD - 1 + kd; ++waited) {
               int s = pslot + waited;
               uint32_t p = pph;
@@ -385,12 +391,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                 ptx::umma_commit(&bEmpty[bst]);
                 // planes whose last reader was this kd group go back to the producer
                 if (khw == KS * KS - 1) {
-                  if (kd < KS - 1) {
+                  if (kd < KSD - 1) {
                     int s = pslot + kd;
                     if (s >= C::NSLOT) s -= C::NSLOT;
                     ptx::umma_commit(&planeEmpty[s]);
                   } else {
-                    for (int i = KS - 1; i < C::PPC; ++i) {
+                    for (int i = KSD - 1; i < C::PPC; ++i) {
                       int s = pslot + i;
                       if (s >= C::NSLOT) s -= C::NSLOT;
                       ptx::umma_commit(&planeEmpty[s]);
@@ -432,7 +438,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
           rs[i] = __ldg(mr + args.cin_total + i);
         }
         for (int i = 0; i < C::PPC; ++i) {
-          const int d = t.d0 - C::PAD + i;
+          const int d = t.d0 - C::PAD_D + i;
           const bool plane_valid = d >= 0 && d < args.D;
           ptx::mbar_wait(&planeFull[slot], ph);
           uint8_t* pl = smA + slot * C::PLANE_BYTES;
@@ -585,7 +591,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         }
         ptx::named_bar_sync(1, 128);
         const int e = threadIdx.x - 128;  // 0..127
-        for (int i = e; i < 2 * BN; i += 128) {
+        for (int i = e; args.stats_partial != nullptr && i < 2 * BN; i += 128) {
           const float s = (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
           const int which = i / BN, col = i - which * BN;
           args.stats_partial[(static_cast<size_t>(t.spatial) * 2 + which) * args.ldo + t.n_tile * BN + col] = s;
@@ -699,10 +705,10 @@ static int make_convT_out_tmap(CUtensorMap* m, const void* base, int ld, int W2,
   return 0;
 }
 
-template <int KS, int BN, int TD, int MODE, bool STACK, bool XF, bool BF16 = false>
+template <int KS, int BN, int TD, int MODE, bool STACK, bool XF, bool BF16 = false, int KSD = KS>
 static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvTcArgs& a, int smem_bytes,
                       cudaStream_t stream) {
-  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK, XF, BF16>;
+  auto kern = conv3d_tc_kernel<KS, BN, TD, MODE, STACK, XF, BF16, KSD>;
   static bool attr_set[64] = {false};
   if (first_use_on_device(attr_set))
     NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -713,9 +719,9 @@ static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvT
   return 0;
 }
 
-template <int KS, int BN, int TD, int MODE, bool STACK = false, bool BF16 = false>
+template <int KS, int BN, int TD, int MODE, bool STACK = false, bool BF16 = false, int KSD = KS>
 static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
-  using C = ConvCfg<KS, BN, TD, STACK, MODE == 1>;
+  using C = ConvCfg<KS, BN, TD, STACK, MODE == 1, KSD>;
   CUtensorMap tm, tmo;
   if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H, BF16)) return rc;
   if constexpr (MODE == 1) {
@@ -728,8 +734,8 @@ static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream)
   a.tiles_d = (a.D + TD - 1) / TD;
   a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
   a.cin_total = Cin;
-  if constexpr (BF16) {
-    return launch_one<KS, BN, TD, MODE, STACK, false, true>(tm, tmo, a, C::SMEM_BYTES, stream);
+  if constexpr (BF16 || KSD != KS || KS == 5) {
+    return launch_one<KS, BN, TD, MODE, STACK, false, BF16, KSD>(tm, tmo, a, C::SMEM_BYTES, stream);
   } else {
     if (a.in_mr) return launch_one<KS, BN, TD, MODE, STACK, true>(tm, tmo, a, C::SMEM_BYTES, stream);
     return launch_one<KS, BN, TD, MODE, STACK, false>(tm, tmo, a, C::SMEM_BYTES, stream);
@@ -782,6 +788,35 @@ int conv3d_k3_dgrad(const void* dy, int NB, int D, int H, int W, int Cout, const
   if (Cin % 128) return set_error("conv3d_k3_dgrad: Cin must be 64 or a multiple of 128");
   a.n_tiles = Cin / 128;
   return launch_cfg<3, 128, 2, 0, false, true>(dy, a, Cout, stream);
+}
+
+// Generic 64 -> 64 stride-1 "same" convolution for DeepLinearGenerator (reference models/networks.py:893-917): the
+// k5 layer (ksd = ksp = 5) and the k7 Cin = 1 layer as a 7-tap depth conv over a 49(+15)-channel in-plane im2col
+// (ksd = 7, ksp = 1).  fmt 0: fp16 in / out (forward), 1: bf16 (data gradient, packed with flip).  No statistics.
+int conv3d_tc_64(const void* x, int fmt, int NB, int D, int H, int W, const void* wpacked, int ksd, int ksp, void* y,
+                 cudaStream_t stream) {
+  ConvTcArgs a{};
+  a.W = W, a.H = H, a.D = D, a.NB = NB;
+  a.chunks = 1;
+  a.wpacked = static_cast<const uint8_t*>(wpacked);
+  a.out_raw = static_cast<__half*>(y);
+  a.ldo = 64;
+  a.n_tiles = 1;
+  if (ksd == 5 && ksp == 5)
+    return fmt ? launch_cfg<5, 64, 2, 0, false, true>(x, a, 64, stream) : launch_cfg<5, 64, 2, 0>(x, a, 64, stream);
+  if (ksd == 7 && ksp == 1)
+    return fmt ? launch_cfg<1, 64, 4, 0, false, true, 7>(x, a, 64, stream)
+               : launch_cfg<1, 64, 4, 0, false, false, 7>(x, a, 64, stream);
+  return set_error("conv3d_tc_64: unsupported filter %d x %d x %d", ksd, ksp, ksp);
+}
+
+// Generic (unstacked, N tile 64) packed image of w = (Cout = 64, Cin = 64, taps) fp32; dgrad: channel-transposed,
+// tap-reversed, bf16.
+int pack_weights_64(const float* w, void* out, int taps, int dgrad, cudaStream_t stream) {
+  pack_weights_kernel<<<num_sms() * 4, 256, 0, stream>>>(w, static_cast<uint16_t*>(out), 64, 64, taps, 64, 0, 0,
+                                                         dgrad);
+  NC_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // Data gradient of ConvTranspose3d(k2, s2): with the output gradient gathered space-to-depth into

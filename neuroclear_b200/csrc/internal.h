@@ -52,8 +52,17 @@ int in_relu_bwd(const void* raw, const float* mean_rstd, int NB, int D, int H, i
                 float* scratch, float* m12, void* d_raw, cudaStream_t stream);
 int head_bwd(const void* raw, const float* mean_rstd, const float* hp, const float* dout, int NB, int D, int H, int W,
              float* du, float* scratch, float* grads, cudaStream_t stream);
-int conv1_wgrad(const float* x, const void* dy, int NB, int D, int H, int W, float* scratch, float* dw,
+int conv1_wgrad(const float* x, const void* dy, int dy_fmt, int NB, int D, int H, int W, float* scratch, float* dw,
                 cudaStream_t stream);
+// deeplinear.cu
+int im2col49(const float* x, int NB, int D, int H, int W, int fmt, void* out, cudaStream_t stream);
+int col2im49(const void* g, int NB, int D, int H, int W, float* dx, cudaStream_t stream);
+int stencil64to1_fwd(const void* h, const float* K, int NB, int D, int H, int W, float* out, cudaStream_t stream);
+int stencil64to1_bwd_data(const float* dout, const float* K, int NB, int D, int H, int W, void* dh,
+                          cudaStream_t stream);
+int conv3d_tc_64(const void* x, int fmt, int NB, int D, int H, int W, const void* wpacked, int ksd, int ksp, void* y,
+                 cudaStream_t stream);
+int pack_weights_64(const float* w, void* out, int taps, int dgrad, cudaStream_t stream);
 int space_to_depth_bf16(const void* src, int ld, int coff, int NB, int D, int H, int W, int C, void* out,
                         cudaStream_t stream);
 int colsum_bf16(const void* src, int ld, int coff, int NB, long long rows, int C, float* scratch, float* out,

@@ -294,8 +294,9 @@ head_bwd_kernel(const __half* __restrict__ raw, const float* __restrict__ mr, co
 // ------------------------------------------------------------------------------------------------ first layer wgrad
 // dW[co][tap] = sum_v dy[v][co] * x[v + tap - 1] for the Cin = 1 k3 conv (networks.py:420).  Thread = 4 output
 // channels x 27 taps in registers; 16 voxel lanes per block are combined in lane order.
+template <bool F16>
 __global__ void __launch_bounds__(256)
-conv1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int D, int H, int W,
+conv1_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dy, int D, int H, int W,
                    float* __restrict__ partial) {
   __shared__ float acc_s[27 * 64];
   const int nb = blockIdx.y;
@@ -312,8 +313,14 @@ conv1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict_
     const unsigned r = v / W;
     const int h = r % H, d = r / H;
     const uint2 rawg = __ldg(reinterpret_cast<const uint2*>(dy + (static_cast<size_t>(nb) * voxels + v) * 64 + g * 4));
-    const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&rawg);
-    const float2 ga = __bfloat1622float2(g2[0]), gb = __bfloat1622float2(g2[1]);
+    float2 ga, gb;
+    if constexpr (F16) {
+      const __half2* g2 = reinterpret_cast<const __half2*>(&rawg);
+      ga = __half22float2(g2[0]), gb = __half22float2(g2[1]);
+    } else {
+      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&rawg);
+      ga = __bfloat1622float2(g2[0]), gb = __bfloat1622float2(g2[1]);
+    }
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
       const int zd = d + kd - 1;
@@ -482,12 +489,17 @@ int head_bwd(const void* raw, const float* mean_rstd, const float* hp, const flo
   return 0;
 }
 
-// scratch: bwd_blocks() / 4 * NB * 1728 floats; dw: (64, 27), summed over samples
-int conv1_wgrad(const float* x, const void* dy, int NB, int D, int H, int W, float* scratch, float* dw,
+// scratch: bwd_blocks() / 4 * NB * 1728 floats; dw: (64, 27), summed over samples; dy_fmt 0 = fp16, 1 = bf16
+int conv1_wgrad(const float* x, const void* dy, int dy_fmt, int NB, int D, int H, int W, float* scratch, float* dw,
                 cudaStream_t stream) {
   if (static_cast<long long>(D) * H * W >= (1ll << 31)) return set_error("conv1_wgrad: cube too large");
   const int blocks = bwd_blocks() / 4;
-  conv1_wgrad_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(x, static_cast<const __nv_bfloat16*>(dy), D, H, W, scratch);
+  if (dy_fmt)
+    conv1_wgrad_kernel<false><<<dim3(blocks, NB), 256, 0, stream>>>(x, static_cast<const uint16_t*>(dy), D, H, W,
+                                                                    scratch);
+  else
+    conv1_wgrad_kernel<true><<<dim3(blocks, NB), 256, 0, stream>>>(x, static_cast<const uint16_t*>(dy), D, H, W,
+                                                                   scratch);
   NC_CUDA(cudaGetLastError());
   colsum_finalize_kernel<<<dim3(1728 / 32, 1), 256, 0, stream>>>(scratch, blocks * NB, 1728, 1.0, dw);
   NC_CUDA(cudaGetLastError());

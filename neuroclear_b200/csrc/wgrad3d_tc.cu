@@ -28,9 +28,11 @@ constexpr int TW = 8;
 constexpr int TH = 16;
 constexpr int MAX_PAIRS = 8;  // 8 x 64 fp32 columns = all 512 TMEM columns
 
-template <int KS>
+// KS = in-plane filter extent, KSD = extent along d (see ConvCfg in conv3d_tc.cu)
+template <int KS, int KSD = KS>
 struct WgCfg {
   static constexpr int PAD = KS / 2;
+  static constexpr int PAD_D = KSD / 2;
   static constexpr int HALO_W = TW + KS - 1;
   static constexpr int HALO_H = TH + KS - 1;
   static constexpr int PLANE_ROWS = HALO_W * HALO_H;
@@ -59,11 +61,11 @@ struct WgArgs {
   float* partial;  // [splits][KS^3][Cout][Cin]
 };
 
-template <int KS>
+template <int KS, int KSD>
 __global__ void __launch_bounds__(256, 1)
 wgrad3d_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapDy,
                   const WgArgs args) {
-  using C = WgCfg<KS>;
+  using C = WgCfg<KS, KSD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* aux = smem + C::NSTAGE * C::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(aux);
@@ -79,8 +81,8 @@ wgrad3d_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
   const int split = blockIdx.x - item * args.splits;
   const int grp = item % C::GROUPS;
   item /= C::GROUPS;
-  const int kd = item % KS;
-  item /= KS;
+  const int kd = item % KSD;
+  item /= KSD;
   const int cout_blocks = args.Cout / 64;
   const int cb = item % cout_blocks;
   const int cc = item / cout_blocks;
@@ -124,7 +126,8 @@ wgrad3d_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
         uint8_t* stage = smem + st * C::STAGE_BYTES;
         ptx::mbar_wait(&empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&full[st], C::PLANE_BOX_BYTES + C::DY_BYTES);
-        ptx::tma_load_5d(stage, &tmapX, &full[st], cc * 64, wt * TW - C::PAD, ht * TH - C::PAD, d + kd - C::PAD, nb);
+        ptx::tma_load_5d(stage, &tmapX, &full[st], cc * 64, wt * TW - C::PAD, ht * TH - C::PAD, d + kd - C::PAD_D,
+                         nb);
         ptx::tma_load_5d(stage + C::PLANE_BYTES, &tmapDy, &full[st], cb * 64, wt * TW, ht * TH, d, nb);
         if (++st == C::NSTAGE) {
           st = 0;
@@ -187,7 +190,7 @@ wgrad3d_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
     ptx::mbar_wait(accFull, 0);
     ptx::tc_fence_after();
     const bool any = pt_end > pt_begin;  // an empty split never issued an MMA: its accumulators are undefined
-    const size_t per_split = static_cast<size_t>(KS * KS * KS) * args.Cout * args.Cin;
+    const size_t per_split = static_cast<size_t>(KSD * KS * KS) * args.Cout * args.Cin;
     float* base = args.partial + per_split * split;
     for (int p = 0; p < pairs; ++p) {
       const int t = 2 * p + (m >> 6);
@@ -248,26 +251,31 @@ int make_tmap(CUtensorMap* m, const void* base, int fmt, int C, int W, int H, in
   return 0;
 }
 
-template <int KS>
+template <int KS, int KSD = KS>
 int wgrad_items(int Cin, int Cout) {
-  return (Cin / 64) * (Cout / 64) * KS * WgCfg<KS>::GROUPS;
+  return (Cin / 64) * (Cout / 64) * KSD * WgCfg<KS, KSD>::GROUPS;
 }
 
+// ks = 71 selects the (ksd = 7, ksp = 1) filter of the im2col'ed k7 Cin = 1 layer
 int items_for(int ks, int Cin, int Cout) {
-  return ks == 1 ? wgrad_items<1>(Cin, Cout) : ks == 3 ? wgrad_items<3>(Cin, Cout) : wgrad_items<5>(Cin, Cout);
+  return ks == 1    ? wgrad_items<1>(Cin, Cout)
+         : ks == 3  ? wgrad_items<3>(Cin, Cout)
+         : ks == 5  ? wgrad_items<5>(Cin, Cout)
+                    : wgrad_items<1, 7>(Cin, Cout);
 }
+int taps_for(int ks) { return ks == 71 ? 7 : ks * ks * ks; }
 
-template <int KS>
+template <int KS, int KSD = KS>
 int launch(const void* x, int x_fmt, const void* dy, int dy_fmt, WgArgs a, cudaStream_t stream) {
-  using C = WgCfg<KS>;
+  using C = WgCfg<KS, KSD>;
   CUtensorMap tx, tdy;
   if (int rc = make_tmap(&tx, x, x_fmt, a.Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::HALO_H)) return rc;
   if (int rc = make_tmap(&tdy, dy, dy_fmt, a.Cout, a.W, a.H, a.D, a.NB, TW, TH)) return rc;
-  auto kern = wgrad3d_tc_kernel<KS>;
+  auto kern = wgrad3d_tc_kernel<KS, KSD>;
   static bool attr_set[64] = {false};
   if (first_use_on_device(attr_set))
     NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  kern<<<wgrad_items<KS>(a.Cin, a.Cout) * a.splits, 256, C::SMEM_BYTES, stream>>>(tx, tdy, a);
+  kern<<<wgrad_items<KS, KSD>(a.Cin, a.Cout) * a.splits, 256, C::SMEM_BYTES, stream>>>(tx, tdy, a);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -288,12 +296,13 @@ static long long wgrad_plane_tiles(int NB, int D, int H, int W) {
 
 size_t conv3d_wgrad_scratch_bytes(int ks, int NB, int D, int H, int W, int Cin, int Cout) {
   const int s = conv3d_wgrad_splits(ks, Cin, Cout, wgrad_plane_tiles(NB, D, H, W));
-  return static_cast<size_t>(s) * ks * ks * ks * Cin * Cout * sizeof(float);
+  return static_cast<size_t>(s) * taps_for(ks) * Cin * Cout * sizeof(float);
 }
 
 int conv3d_wgrad(const void* x, int x_fmt, const void* dy, int dy_fmt, int NB, int D, int H, int W, int Cin,
                  int Cout, int ks, void* scratch, float* dw, cudaStream_t stream) {
-  if (ks != 1 && ks != 3 && ks != 5) return set_error("conv3d_wgrad: kernel size must be 1, 3 or 5");
+  if (ks != 1 && ks != 3 && ks != 5 && ks != 71)
+    return set_error("conv3d_wgrad: kernel size must be 1, 3, 5 or 71 (= 7 x 1 x 1)");
   if (Cin % 64 || Cout % 64) return set_error("conv3d_wgrad: Cin and Cout must be multiples of 64");
   if ((x_fmt | dy_fmt) & ~1) return set_error("conv3d_wgrad: operand format must be 0 (fp16) or 1 (bf16)");
   WgArgs a{};
@@ -308,9 +317,10 @@ int conv3d_wgrad(const void* x, int x_fmt, const void* dy, int dy_fmt, int NB, i
             (static_cast<uint32_t>(dy_fmt) << 10) | (1u << 15) | (1u << 16);
   if (int rc = (ks == 1   ? launch<1>(x, x_fmt, dy, dy_fmt, a, stream)
                 : ks == 3 ? launch<3>(x, x_fmt, dy, dy_fmt, a, stream)
-                          : launch<5>(x, x_fmt, dy, dy_fmt, a, stream)))
+                : ks == 5 ? launch<5>(x, x_fmt, dy, dy_fmt, a, stream)
+                          : launch<1, 7>(x, x_fmt, dy, dy_fmt, a, stream)))
     return rc;
-  const int taps = ks * ks * ks;
+  const int taps = taps_for(ks);
   wgrad_reduce_kernel<<<num_sms() * 2, 256, 0, stream>>>(a.partial, a.splits, taps, Cout, Cin, dw);
   NC_CUDA(cudaGetLastError());
   return 0;

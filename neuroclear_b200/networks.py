@@ -185,12 +185,75 @@ class Unet_deconv(nn.Module):
             return eng.forward(x)[:, None]
 
 
+class _DeepLinearFn(torch.autograd.Function):
+    """DeepLinearGenerator under autograd on neuroclear_b200.deeplinear_engine (input gradient included)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module.engine()
+        with torch.cuda.device(x.device):
+            y = eng.forward(x.detach().to(torch.float32)[:, 0].contiguous())
+        ctx.module, ctx.eng, ctx.saved = module, eng, eng.saved
+        eng.saved = None
+        return y[:, None]
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.eng
+        eng.saved, ctx.saved = ctx.saved, None
+        with torch.cuda.device(dy.device):
+            dx, grads = eng.backward(dy[:, 0].contiguous())
+        return (None, dx[:, None]) + tuple(grads[k] for k, _ in ctx.module.named_parameters())
+
+
+class DeepLinearGenerator(nn.Module):
+    """reference networks.py:893-917 (same children, same state_dict) on sm_100a kernels."""
+
+    def __init__(self, input_nc, output_nc):
+        super().__init__()
+        if input_nc != 1 or output_nc != 1:
+            raise NotImplementedError("the B200 path implements the 1-channel deep_linear_gen of the reference")
+        self.first_layer = nn.Conv3d(1, 64, 7, padding=3, bias=False)
+        self.feature_block = nn.Sequential(nn.Conv3d(64, 64, 5, padding=2, bias=False),
+                                           nn.Conv3d(64, 64, 3, padding=1, bias=False),
+                                           nn.Conv3d(64, 32, 1, bias=False), nn.Conv3d(32, 16, 1, bias=False))
+        self.final_layer = nn.Conv3d(16, 1, 1, bias=False)
+        self._engine = None
+        self._engine_sig = None
+
+    def engine(self):
+        from .deeplinear_engine import DeepLinearEngine
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise NeuroclearError("DeepLinearGenerator (B200): parameters are on the CPU; there is no CPU fallback")
+        sig = tuple((q.data_ptr(), q._version) for q in self.parameters())
+        if self._engine is None or self._engine.device != p.device:
+            self._engine, self._engine_sig = DeepLinearEngine(p.device), None
+        if self._engine_sig != sig:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_sig = sig
+        return self._engine
+
+    def forward(self, input):
+        if input.dim() != 5 or input.shape[1] != 1:
+            raise NeuroclearError("DeepLinearGenerator expects (N, 1, D, H, W)")
+        if not input.is_cuda:
+            raise NeuroclearError("DeepLinearGenerator (B200): input is on the CPU; there is no CPU fallback")
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return _DeepLinearFn.apply(self, input, *self.parameters())
+        with torch.cuda.device(input.device):
+            return self.engine().forward(input.detach().to(torch.float32)[:, 0].contiguous(), keep=False)[:, None]
+
+
 def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, init_type="normal", init_gain=0.02,
              gpu_ids=[], kernel_size=9, given_psf=None, noise_setting=None, dimension=3):
-    """reference networks.py:140-197; only the generator on the hot path is provided."""
+    """reference networks.py:140-197; the two generators on the hot path are provided."""
     norm_layer = get_norm_layer(norm_type=norm, dimension=dimension)
     if netG == "unet_deconv":
         net = Unet_deconv(1, output_nc, norm_layer=norm_layer, dimension=dimension)  # input_nc hard-coded 1 (:174)
+    elif netG == "deep_linear_gen":
+        net = DeepLinearGenerator(input_nc, output_nc)                               # networks.py:193-194
     else:
-        raise NotImplementedError("Generator model name [%s] is not on the B200 hot path (only unet_deconv is)" % netG)
+        raise NotImplementedError("Generator model name [%s] is not on the B200 hot path (unet_deconv and "
+                                  "deep_linear_gen are)" % netG)
     return init_net(net, init_type, init_gain, gpu_ids)

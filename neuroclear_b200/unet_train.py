@@ -283,7 +283,7 @@ class UnetDeconvTrainEngine:
         del d2, a1, dcat1, dp1
         d1 = in_bwd(_FIRST, 0, 64, 0, grad=dA1, ld=64, coff=0)
         dw1 = e(64 * 27, f32)
-        call("nc_conv3d_cin1_k3_wgrad", ptr(sv["x"]), ptr(d1), nb, *dims[0], ptr(scratch), ptr(dw1), s)
+        call("nc_conv3d_cin1_k3_wgrad", ptr(sv["x"]), ptr(d1), 1, nb, *dims[0], ptr(scratch), ptr(dw1), s)
         grads[_FIRST + ".weight"] = dw1.view(64, 1, 3, 3, 3)
         grads[_FIRST + ".bias"] = torch.zeros(64, dtype=f32, device=dev)
         self.saved = None

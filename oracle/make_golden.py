@@ -149,6 +149,35 @@ def golden_unet_grad():
     np.savez_compressed(os.path.join(GOLD, "unet_grad.npz"), **out)
 
 
+def golden_deeplinear():
+    """Reference DeepLinearGenerator (networks.define_G('deep_linear_gen')) forward + autograd on a 12x20x16 crop vs
+    the oracle; records output, input gradient and sampled weight gradients."""
+    rh.install()
+    from models import networks
+    from oracle import deeplinear
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "deep_linear_gen", "instance", False, "kaiming", 0.02, [], dimension=3)
+    ref_sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in ref_sd.items()} == deeplinear.STATE_DICT_SHAPES
+    assert sum(v.numel() for v in ref_sd.values()) == deeplinear.N_PARAMS
+    sd = deeplinear.random_state_dict(seed=2)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand((1, 1, 12, 20, 16), generator=g).requires_grad_(True)
+    dout = torch.randn((1, 1, 12, 20, 16), generator=g) * 1e-3
+    y = net(x)
+    y.backward(dout)
+    y_or, dx_or, g_or = deeplinear.deep_linear_gradients(x.detach(), sd, dout)
+    assert (y.detach() - y_or).abs().max().item() <= 1e-5
+    assert (x.grad - dx_or).abs().max().item() <= 1e-5 * dx_or.abs().max().item() + 1e-9
+    out = {"x": x.detach().numpy(), "dout": dout.numpy(), "y": y.detach().numpy(), "dx": x.grad.numpy(),
+           "w_checksum": np.array([float(sum(v.double().sum() for v in sd.values()))])}
+    for k, prm in net.named_parameters():
+        assert (prm.grad - g_or[k]).abs().max().item() <= 1e-4 * prm.grad.abs().max().item(), k
+        out["gsample_" + k] = prm.grad.numpy().reshape(-1)[::GRAD_SAMPLE_STRIDE].copy()
+    np.savez_compressed(os.path.join(GOLD, "deeplinear_grad.npz"), **out)
+
+
 def golden_mip():
     rh.install()
     from models.axial_to_lateral_gan_apollo_model import Volume
@@ -281,6 +310,7 @@ def main():
     golden_dice_assemble()
     golden_unet()
     golden_unet_grad()
+    golden_deeplinear()
     golden_mip()
     golden_discriminator()
     golden_apollo_discriminator_path()

@@ -259,7 +259,7 @@ def test_first_layer_wgrad():
     scratch = torch.empty(lib.nc_bwd_scratch_bytes(nb) // 4, dtype=torch.float32, device="cuda")
     dw = torch.empty((64, 27), dtype=torch.float32, device="cuda")
     x_dev, dy_dev = x[:, 0].contiguous().cuda(), ndhwc(dy, torch.bfloat16)
-    L.call("nc_conv3d_cin1_k3_wgrad", L.ptr(x_dev), L.ptr(dy_dev), nb, d, h, w, L.ptr(scratch), L.ptr(dw),
+    L.call("nc_conv3d_cin1_k3_wgrad", L.ptr(x_dev), L.ptr(dy_dev), 1, nb, d, h, w, L.ptr(scratch), L.ptr(dw),
            L.stream_ptr())
     torch.cuda.synchronize()
     check_grad("dW first layer", dw.cpu(), wt.grad.reshape(64, 27), rel=1e-4, mx=1e-4)

@@ -115,3 +115,31 @@ def test_discriminator_matches_reference_module():
     assert np.abs(x.grad.numpy() - f["dx"]).max() <= 1e-7
     for k in sd:
         assert np.abs(sd[k].grad.numpy().reshape(-1)[::61] - f["dsample_" + k]).max() <= 1e-6
+
+
+def test_deeplinear_oracle_matches_reference_fixture():
+    """oracle/deeplinear.py vs the output / gradients recorded from the reference DeepLinearGenerator"""
+    from oracle import deeplinear
+    z = np.load(os.path.join(GOLDEN, "deeplinear_grad.npz"))
+    sd = deeplinear.random_state_dict(seed=2)
+    y, dx, grads = deeplinear.deep_linear_gradients(torch.from_numpy(z["x"]), sd, torch.from_numpy(z["dout"]))
+    assert float((y - torch.from_numpy(z["y"])).abs().max()) <= 1e-5
+    assert float((dx - torch.from_numpy(z["dx"])).abs().max()) <= 1e-7
+    for k in deeplinear.STATE_DICT_SHAPES:
+        ref = torch.from_numpy(z["gsample_" + k])
+        got = grads[k].reshape(-1)[::61]
+        assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()), k
+
+
+def test_unet_gradient_oracle_matches_reference_fixture():
+    """oracle/unet.py::unet_deconv_gradients vs the gradients recorded from the reference Unet_deconv (8^3 would be
+    cheaper, but the fixture's 16x24x32 crop is what the GPU test uses; ~10 s on the CPU)"""
+    from oracle import unet
+    z = np.load(os.path.join(GOLDEN, "unet_grad.npz"))
+    sd = unet.random_state_dict(seed=4, bias_std=0.1)
+    y, grads = unet.unet_deconv_gradients(torch.from_numpy(z["x"]), sd, torch.from_numpy(z["dout"]))
+    assert float((y - torch.from_numpy(z["y"])).abs().max()) <= 1e-6
+    for k in unet.STATE_DICT_SHAPES:
+        ref = torch.from_numpy(z["gsample_" + k])
+        got = grads[k].reshape(-1)[::61]
+        assert float((got - ref).abs().max()) <= 1e-4 * max(float(z["gnorm_" + k][1]), 1e-7), k
