@@ -1,0 +1,86 @@
+"""The training step of the reference's AxialToLateralGANApolloModel (models/axial_to_lateral_gan_apollo_model.py)
+on the B200 path: G_A = unet_deconv, G_B = deep_linear_gen (README training command), four 2-D PatchGAN
+discriminators on slices / max-intensity projections, LSGAN + L1 cycle loss, two Adam optimisers.
+
+Same protocol as the reference model: set_input(dict) -> optimize_parameters() -> get_current_losses(), attributes
+real / fake / rec / loss_*, the same host np.random draw order (projection depth in set_input, then slice / start
+indices in backward_G, backward_D_*).  Everything numeric runs on the hand-written kernels: the generators through
+networks.define_G (tcgen05 convs forward and backward), the projection / discriminator path through
+ApolloDiscriminatorPath, the updates through nc_adam_step.  One process drives one GPU; under torch.distributed the
+gradients of both optimisers are averaged over the ranks with one flat-bucket all-reduce each (data parallel,
+SURVEY.md §8e)."""
+from __future__ import annotations
+
+import itertools
+from collections import OrderedDict
+
+import torch
+
+from . import networks
+from .apollo_d_path import ApolloDiscriminatorPath, FusedAdam, allreduce_mean_gradients
+
+LOSS_NAMES = ["D_A_lateral", "D_A_axial", "G_A", "G_A_lateral", "G_A_axial", "cycle",
+              "D_B_lateral", "D_B_axial", "G_B", "G_B_lateral", "G_B_axial"]      # apollo_model.py:61-62
+
+
+class AxialToLateralGANApolloModel:
+    def __init__(self, opt, device=None, group=None, distributed=None):
+        import torch.distributed as dist
+        self.opt = opt
+        gpu_ids = list(getattr(opt, "gpu_ids", [0])) or [0]
+        self.device = torch.device(device if device is not None else "cuda:%d" % gpu_ids[0])
+        self.group = group
+        self.distributed = dist.is_initialized() if distributed is None else distributed
+        ids = [self.device.index if self.device.index is not None else torch.cuda.current_device()]
+        self.loss_names = list(LOSS_NAMES)
+        self.netG_A = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.netG, opt.norm, not opt.no_dropout,
+                                        opt.init_type, opt.init_gain, ids, dimension=3)          # :91-93
+        self.netG_B = networks.define_G(opt.output_nc, opt.input_nc, opt.ngf, opt.netG_B, opt.norm,
+                                        not opt.no_dropout, opt.init_type, opt.init_gain, ids, dimension=3)   # :95-97
+        self.dpath = ApolloDiscriminatorPath(opt, self.device, group=group, distributed=self.distributed)   # :99-136
+        for n in ("D_A_axial", "D_A_lateral", "D_B_axial", "D_B_lateral"):
+            setattr(self, "net" + n, getattr(self.dpath, "net" + n))
+        self.optimizer_G = FusedAdam(itertools.chain(self.netG_A.parameters(), self.netG_B.parameters()),
+                                     lr=opt.lr, betas=(opt.beta1, 0.999))                        # :131-132
+        self.optimizer_D = self.dpath.optimizer_D
+        self.optimizers = [self.optimizer_G, self.optimizer_D]
+
+    # ---- :142-160
+    def set_input(self, input):
+        a_to_b = getattr(self.opt, "direction", "AtoB") == "AtoB"
+        self.real = input["A" if a_to_b else "B"].to(self.device)
+        self.image_paths = input["A_paths" if a_to_b else "B_paths"]
+        self.projection_depth = self.dpath.draw_projection_depth()
+
+    # ---- :162-167
+    def forward(self):
+        self.fake = self.netG_A(self.real)
+        self.rec = self.netG_B(self.fake)
+
+    def test(self):
+        with torch.no_grad():
+            self.forward()
+
+    # ---- :255-283
+    def backward_G(self):
+        self.loss_G = self.dpath.generator_losses(self.real, self.fake, self.rec)
+        self.loss_G.backward()
+
+    # ---- :285-307
+    def optimize_parameters(self):
+        self.forward()
+        self.optimizer_G.zero_grad()
+        self.backward_G()                       # the Ds are frozen inside generator_losses (set_requires_grad False)
+        if self.distributed:
+            allreduce_mean_gradients(self.optimizer_G.params, self.group)
+        self.optimizer_G.step()
+        self.dpath.optimize_D(self.real, self.fake.detach(), self.rec.detach())
+
+    def get_current_losses(self):
+        out = OrderedDict()
+        for name in self.loss_names:
+            out[name] = float(getattr(self.dpath, "loss_" + name))
+        return out
+
+    def get_current_visuals(self):
+        return OrderedDict((k, getattr(self, k)) for k in ("real", "fake", "rec"))

@@ -59,7 +59,7 @@ class DeepLinearEngine:
             self.tail = [f(k) for k in KEYS[2:]]
             self.K = fold_tail(*self.tail)
             self.w = pk
-            torch.cuda.current_stream().synchronize()
+            # no synchronisation: the fp32 staging copies are freed in stream order (same stream as the packers)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, keep=True):

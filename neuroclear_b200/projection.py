@@ -59,7 +59,13 @@ class Volume:
         start = np.random.randint(0, self.num_slice - depth)        # apollo_model.py:340
         if self.volume.dtype != torch.float32:
             raise NeuroclearError("Volume.get_projection expects float32")
-        return _MipFn.apply(self.volume, slice_axis, int(start), int(depth))
+        # the reference slices [start : start + depth] along the axis: on a non-cubic crop (num_slice is the LAST
+        # extent, :325) python slicing silently truncates at the end of the axis, and an empty slab makes torch.max fail
+        size = self.volume.shape[slice_axis + 2]
+        depth = min(int(depth), size - int(start))
+        if depth <= 0:
+            raise NeuroclearError("Volume.get_projection: empty slab (start %d on an axis of %d planes)" % (start, size))
+        return _MipFn.apply(self.volume, slice_axis, int(start), depth)
 
     def get_volume(self):
         return self.volume

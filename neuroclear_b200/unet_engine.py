@@ -88,7 +88,7 @@ class UnetDeconvEngine:
                 self.bias[prefix] = f(prefix + ".bias")
             self.head = torch.cat([f("one_by_one.weight").reshape(64), f("one_by_one.bias").reshape(1),
                                    f("one_by_one_2.weight").reshape(1), f("one_by_one_2.bias").reshape(1)]).contiguous()
-            torch.cuda.current_stream().synchronize()  # the fp32 staging copies die here
+            # no synchronisation: the fp32 staging copies are freed in stream order (same stream as the packers)
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, nb, d, h, w):

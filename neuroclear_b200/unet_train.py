@@ -58,7 +58,7 @@ class UnetDeconvTrainEngine:
                 out = torch.empty(8 * cout * cin * 2, dtype=torch.uint8, device=dev)
                 call("nc_pack_weights_convT3d_k2s2_dgrad", ptr(w), cin, cout, ptr(out), stream_ptr())
                 self.packed_dgrad[prefix] = out
-            torch.cuda.current_stream().synchronize()
+            # no synchronisation: the fp32 staging copies are freed in stream order (same stream as the packers)
 
     # ------------------------------------------------------------------ forward (keeps raw outputs + statistics)
     def forward(self, x):

@@ -302,6 +302,40 @@ def golden_apollo_discriminator_path():
     np.savez_compressed(os.path.join(GOLD, "apollo_d_path_32.npz"), **out)
 
 
+def golden_apollo_step():
+    """One full optimize_parameters() of the REFERENCE AxialToLateralGANApolloModel (unet_deconv + deep_linear_gen +
+    4 basic Ds, lsgan, lambda_A 5, randomized projection depth 10 — the README training command) on a 32^3 crop, CPU
+    fp32, seeded weights and np.random: the 11 losses, fake / rec statistics, sampled generator gradients and the
+    sampled parameters of all six networks after the step."""
+    rh.install()
+    from models.axial_to_lateral_gan_apollo_model import AxialToLateralGANApolloModel
+    from oracle import deeplinear
+    with redirect_stdout(io.StringIO()):
+        m = AxialToLateralGANApolloModel(apollo_opt())
+    m.netG_A.load_state_dict(unet.random_state_dict(seed=21, bias_std=0.05))
+    m.netG_B.load_state_dict(deeplinear.random_state_dict(seed=22))
+    for i, name in enumerate(D_NAMES):
+        getattr(m, "net" + name).load_state_dict(discriminator.random_state_dict(seed=30 + i))
+    np.random.seed(3)
+    real = torch.rand((1, 1, 32, 32, 32), generator=torch.Generator().manual_seed(5))
+    m.set_input({"A": real, "A_paths": "golden"})
+    m.optimize_parameters()
+    out = {"real": real.numpy(), "depth": np.array(m.projection_depth),
+           "fake_sample": m.fake.detach().numpy().reshape(-1)[::GRAD_SAMPLE_STRIDE].copy(),
+           "rec_sample": m.rec.detach().numpy().reshape(-1)[::GRAD_SAMPLE_STRIDE].copy()}
+    for k in m.loss_names:
+        out["loss_" + k] = np.array(float(getattr(m, "loss_" + k)))
+    def sample(t):          # every 61st element; small tensors (<= 4096 elements) in full
+        flat = t.detach().numpy().reshape(-1)
+        return (flat if flat.size <= 4096 else flat[::GRAD_SAMPLE_STRIDE]).copy()
+    for name in ["G_A", "G_B"] + D_NAMES:
+        for k, prm in getattr(m, "net" + name).named_parameters():
+            out["after_%s.%s" % (name, k)] = sample(prm)
+            if name.startswith("G_"):
+                out["grad_%s.%s" % (name, k)] = sample(prm.grad)
+    np.savez_compressed(os.path.join(GOLD, "apollo_step_32.npz"), **out)
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
@@ -314,6 +348,7 @@ def main():
     golden_mip()
     golden_discriminator()
     golden_apollo_discriminator_path()
+    golden_apollo_step()
     print("golden vectors written to", GOLD)
 
 

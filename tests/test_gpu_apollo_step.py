@@ -1,0 +1,110 @@
+"""One full training iteration of the apollo model on the GPU — AxialToLateralGANApolloModel.optimize_parameters():
+G_A (unet_deconv) and G_B (deep_linear_gen) forward + backward on the tcgen05 kernels, the projection / discriminator
+path, both Adam updates — against the fixture recorded from the REFERENCE model on the CPU in fp32
+(tests/golden/apollo_step_32.npz, oracle/make_golden.py::golden_apollo_step).
+
+Tolerances: forward quantities (fake, rec, the 11 losses) 1-2e-2; generator gradients are compared by direction
+(cosine) and relative L2 0.2 — the ReLU-mask effect documented in tests/test_gpu_unet_train.py; the first Adam step
+moves every parameter by ~lr * sign(gradient), so updated parameters agree within 2.1 lr and in the sign of the update
+for the bulk of the elements."""
+import io
+import os
+from argparse import Namespace
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+STRIDE = 61
+
+
+def sample(t):
+    """every 61st element of a tensor — all of them for tensors of <= 4096 elements (as the fixture was recorded)"""
+    flat = t.detach().float().cpu().reshape(-1)
+    return (flat if flat.numel() <= 4096 else flat[::STRIDE]).numpy()
+
+
+D_NAMES = ["D_A_axial", "D_A_lateral", "D_B_axial", "D_B_lateral"]
+NOISE_ONLY = ("double_conv1.convolution", "double_conv2.convolution", "bottom_layer.convolution",
+              "ex_double_conv2.convolution", "ex_conv1_1.convolution")
+LR = 1e-4
+
+
+def _opt():
+    return Namespace(isTrain=True, gpu_ids=[0], gan_mode="lsgan", randomize_projection_depth=True, projection_depth=10,
+                     min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1, ngf=64, ndf=64,
+                     netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3, norm="instance",
+                     no_dropout=True, init_type="kaiming", init_gain=0.02, lr=LR, beta1=0.1, direction="AtoB",
+                     lambda_A=5.0)
+
+
+def _model():
+    from neuroclear_b200.apollo_model import AxialToLateralGANApolloModel
+    from oracle import deeplinear, discriminator, unet
+    with redirect_stdout(io.StringIO()):
+        m = AxialToLateralGANApolloModel(_opt(), "cuda", distributed=False)
+    before = {"G_A": unet.random_state_dict(seed=21, bias_std=0.05), "G_B": deeplinear.random_state_dict(seed=22)}
+    for i, n in enumerate(D_NAMES):
+        before[n] = discriminator.random_state_dict(seed=30 + i)
+    for name, sd in before.items():
+        getattr(m, "net" + name).module.load_state_dict(sd)
+    return m, before
+
+
+def test_optimize_parameters_matches_reference_fixture():
+    z = np.load(os.path.join(GOLD, "apollo_step_32.npz"))
+    m, before = _model()
+    np.random.seed(3)
+    m.set_input({"A": torch.from_numpy(z["real"]), "A_paths": "golden"})
+    assert m.projection_depth == int(z["depth"])
+    m.optimize_parameters()
+    torch.cuda.synchronize()
+    # ---- forward quantities
+    fake = m.fake.detach().float().cpu().reshape(-1)[::STRIDE].numpy()
+    rec = m.rec.detach().float().cpu().reshape(-1)[::STRIDE].numpy()
+    assert np.abs(fake - z["fake_sample"]).max() <= 1e-2
+    assert np.abs(rec - z["rec_sample"]).max() <= 1e-2 * np.abs(z["rec_sample"]).max()
+    losses = m.get_current_losses()
+    print()
+    for k, v in losses.items():
+        ref = float(z["loss_" + k])
+        print("  loss_%-12s %.6f   reference %.6f" % (k, v, ref))
+        assert abs(v - ref) <= 2e-2 * max(1.0, abs(ref)), k
+    # ---- generator gradients and updated parameters
+    for name in ("G_A", "G_B"):
+        net = getattr(m, "net" + name).module
+        cos_w, n_w = [], 0
+        for k, p in net.named_parameters():
+            ref_g = z["grad_%s.%s" % (name, k)].astype(np.float64)
+            got_g = sample(p.grad).astype(np.float64)
+            after = sample(p)
+            assert np.abs(after - z["after_%s.%s" % (name, k)]).max() <= 2.1 * LR, (name, k)
+            if k.endswith(".bias") and k.startswith(NOISE_ONLY):
+                continue
+            cos = float(got_g @ ref_g / (np.linalg.norm(got_g) * np.linalg.norm(ref_g) + 1e-300))
+            rel = float(np.linalg.norm(got_g - ref_g) / (np.linalg.norm(ref_g) + 1e-300))
+            b = sample(before[name][k])
+            agree = float(np.mean(np.sign(after - b) == np.sign(z["after_%s.%s" % (name, k)] - b)))
+            print("  %s %-40s cos %.4f  rel L2 %.3f  update-sign agreement %.3f" % (name, k, cos, rel, agree))
+            assert cos >= 0.97 and rel <= 0.25, (name, k, cos, rel)
+            if ref_g.size >= 100:
+                assert agree >= 0.85, (name, k, agree)
+    # ---- discriminators after their step
+    for name in D_NAMES:
+        for k, p in getattr(m, "net" + name).module.named_parameters():
+            assert np.abs(sample(p) - z["after_%s.%s" % (name, k)]).max() <= 2.1 * LR, (name, k)
+
+
+def test_two_steps_run_and_losses_stay_finite():
+    m, _ = _model()
+    g = torch.Generator().manual_seed(1)
+    np.random.seed(0)
+    for _ in range(2):
+        m.set_input({"A": torch.rand((1, 1, 28, 28, 28), generator=g), "A_paths": "x"})   # cubic, as the reference needs
+        m.optimize_parameters()
+    assert all(np.isfinite(v) for v in m.get_current_losses().values())
+    m.test()
+    assert tuple(m.rec.shape) == (1, 1, 28, 28, 28) and not m.rec.requires_grad

@@ -1,0 +1,50 @@
+"""GPU timing of the full apollo training iteration (BASELINE.json configs[2]/[3]: train_onecube.py
+axial_to_lateral_gan_apollo, unet_deconv + deep_linear_gen + basic D, batch 1, randomized projection depth 10) on a
+random crop: set_input (H2D of the crop) + optimize_parameters(), CUDA events on the launching stream.
+Usage: python tools/bench_apollo_step.py [S=108] [iters=5]"""
+import io
+import json
+import os
+import sys
+from argparse import Namespace
+from contextlib import redirect_stdout
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neuroclear_b200 import _lib  # noqa: E402
+from neuroclear_b200.apollo_model import AxialToLateralGANApolloModel  # noqa: E402
+from neuroclear_b200 import deeplinear_engine, unet_engine  # noqa: E402
+
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 108
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+opt = Namespace(isTrain=True, gpu_ids=[0], gan_mode="lsgan", randomize_projection_depth=True, projection_depth=10,
+                min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1, ngf=64, ndf=64,
+                netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3, norm="instance",
+                no_dropout=True, init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1, direction="AtoB", lambda_A=5.0)
+torch.manual_seed(0)
+np.random.seed(0)
+with redirect_stdout(io.StringIO()):
+    m = AxialToLateralGANApolloModel(opt, "cuda", distributed=False)
+crops = [torch.rand((1, 1, S, S, S)).pin_memory() for _ in range(3)]
+ev = lambda: torch.cuda.Event(enable_timing=True)
+times, launches = [], 0
+for i in range(iters + 3):
+    e0, e1 = ev(), ev()
+    n0 = _lib.LAUNCHES
+    e0.record()
+    m.set_input({"A": crops[i % 3], "A_paths": "synthetic"})
+    m.optimize_parameters()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.LAUNCHES - n0
+    if i >= 3:
+        times.append(e0.elapsed_time(e1))
+ms = sum(times) / len(times)
+flop = 3 * (unet_engine.FLOP_PER_VOXEL + deeplinear_engine.FLOP_PER_VOXEL) * S ** 3      # reference layer FLOPs, fwd + 2x bwd
+losses = m.get_current_losses()
+print(json.dumps({"crop": S, "ms_per_iter": round(ms, 3), "iters_per_s": round(1e3 / ms, 2), "launches": launches,
+                  "reference_flop_tflops": round(flop / ms / 1e9, 1),
+                  "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+                  "finite": all(np.isfinite(v) for v in losses.values())}))
