@@ -288,6 +288,24 @@ int nc_loss_bwd(const float* p, const float* q, float target, int64_t n, int32_t
  * parameter tensor: p, exp_avg m, exp_avg_sq v updated in place from gradient g; `step` counts from 1. */
 int nc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  int32_t step, nc_stream_t stream);
+/* All parameter tensors of one optimiser in a single launch.  table: DEVICE array of `count` entries
+ * { float* p; const float* g; float* m; float* v; int64_t n; } (40 bytes each); same arithmetic as nc_adam_step. */
+int nc_adam_step_multi(const void* table, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,
+                       nc_stream_t stream);
+
+/* The whole 2-D PatchGAN (NLayerDiscriminator, networks.py:1030-1057: conv s2 + LReLU, (conv s2, IN, LReLU) x
+ * (n_layers-1), (conv s1, IN, LReLU), conv s1 -> 1) in one call per direction: the layer loop runs inside the library.
+ * x: float32 (N,1,H,W); weights / biases: HOST arrays of n_layers+2 device pointers (OIHW float32 / float32);
+ * ws: nc_patchgan_ws_floats(...) floats, written by fwd and consumed by bwd; pred: (N,1,h_out,w_out).
+ * bwd: dx (nullable) = gradient w.r.t. the image; dweights / dbiases (HOST arrays of device pointers, nullable
+ * together) = parameter gradients, overwritten. */
+int64_t nc_patchgan_ws_floats(int32_t n, int32_t h, int32_t w, int32_t ndf, int32_t n_layers);
+int nc_patchgan_fwd(const float* x, int32_t n, int32_t h, int32_t w, int32_t ndf, int32_t n_layers,
+                    const float* const* weights, const float* const* biases, float* ws, float* pred,
+                    nc_stream_t stream);
+int nc_patchgan_bwd(const float* x, const float* dpred, int32_t n, int32_t h, int32_t w, int32_t ndf, int32_t n_layers,
+                    const float* const* weights, float* ws, float* dx, float* const* dweights, float* const* dbiases,
+                    nc_stream_t stream);
 
 #ifdef __cplusplus
 }

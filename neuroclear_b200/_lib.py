@@ -51,6 +51,10 @@ SIGNATURES = {
     "nc_conv3d_tc_64": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
     "nc_stencil64to1_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
     "nc_stencil64to1_bwd_data": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+    "nc_adam_step_multi": (C.c_int, [vp, i32, f32, f32, f32, f32, i32, vp]),
+    "nc_patchgan_ws_floats": (i64, [i32, i32, i32, i32, i32]),
+    "nc_patchgan_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "nc_patchgan_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "nc_convT3d_k2s2_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
     "nc_in_stats_scratch_bytes": (i64, [i32, i32]),
     "nc_in_stats_finalize": (C.c_int, [vp, i32, i64, i32, i64, f32, vp, vp, vp]),

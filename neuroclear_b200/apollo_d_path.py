@@ -32,6 +32,8 @@ class FusedAdam:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.state = {}
         self.step_count = 0
+        self._table = None
+        self._table_event = None
 
     def zero_grad(self):
         for p in self.params:
@@ -39,18 +41,35 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
+        """One launch for all tensors: a pinned host table of {p, g, m, v, n} goes to the device asynchronously."""
+        import numpy as np
         self.step_count += 1
-        for p in self.params:
-            if p.grad is None:
-                continue
-            st = self.state.get(p)
-            if st is None:
-                st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
-            g = p.grad.contiguous()
-            with torch.cuda.device(p.device):
-                call("nc_adam_step", ptr(p), ptr(g), ptr(st[0]), ptr(st[1]), i64(p.numel()), f32(self.lr),
-                     f32(self.betas[0]), f32(self.betas[1]), f32(self.eps), self.step_count, stream_ptr())
-            p.add_(0)   # the kernel wrote through a raw pointer: bump the version counter for autograd / caches
+        if self._table_event is not None:
+            self._table_event.synchronize()
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return
+        dev = live[0].device
+        grads = []
+        for p in live:
+            if p not in self.state:
+                self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
+            grads.append(p.grad.contiguous())
+        if self._table is None or self._table.shape[0] < len(live):
+            self._table = torch.empty((len(live), 5), dtype=torch.int64).pin_memory()
+        tab = self._table[:len(live)]
+        tab.numpy()[:] = np.array([[p.data_ptr(), g.data_ptr(), self.state[p][0].data_ptr(),
+                                    self.state[p][1].data_ptr(), p.numel()] for p, g in zip(live, grads)],
+                                  dtype=np.int64)
+        with torch.cuda.device(dev):
+            tab_dev = tab.to(dev, non_blocking=True)
+            call("nc_adam_step_multi", ptr(tab_dev), len(live), f32(self.lr), f32(self.betas[0]), f32(self.betas[1]),
+                 f32(self.eps), self.step_count, stream_ptr())
+            # the pinned table may be rewritten by the next step only after this copy has been consumed
+            self._table_event = torch.cuda.Event()
+            self._table_event.record()
+        for p in live:   # the kernel wrote through raw pointers: bump the version counters (autograd, weight caches)
+            torch.autograd.graph.increment_version(p)
 
 
 def allreduce_mean_gradients(params, group=None):

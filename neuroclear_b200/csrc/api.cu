@@ -156,6 +156,23 @@ int nc_cast_f16_bf16(const void* src, int32_t src_ld, int32_t src_coff, int64_t 
                      int32_t dst_ld, int32_t dst_coff, nc_stream_t stream) {
   return cast_f16_bf16(src, src_ld, src_coff, rows, c, dst, dst_ld, dst_coff, S(stream));
 }
+int64_t nc_patchgan_ws_floats(int32_t n, int32_t h, int32_t w, int32_t ndf, int32_t n_layers) {
+  return patchgan_ws_floats(n, h, w, ndf, n_layers);
+}
+int nc_patchgan_fwd(const float* x, int32_t n, int32_t h, int32_t w, int32_t ndf, int32_t n_layers,
+                    const float* const* weights, const float* const* biases, float* ws, float* pred,
+                    nc_stream_t stream) {
+  return patchgan_fwd(x, n, h, w, ndf, n_layers, weights, biases, ws, pred, S(stream));
+}
+int nc_patchgan_bwd(const float* x, const float* dpred, int32_t n, int32_t h, int32_t w, int32_t ndf, int32_t n_layers,
+                    const float* const* weights, float* ws, float* dx, float* const* dweights, float* const* dbiases,
+                    nc_stream_t stream) {
+  return patchgan_bwd(x, dpred, n, h, w, ndf, n_layers, weights, ws, dx, dweights, dbiases, S(stream));
+}
+int nc_adam_step_multi(const void* table, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,
+                       nc_stream_t stream) {
+  return adam_step_multi(table, count, lr, beta1, beta2, eps, step, S(stream));
+}
 int nc_convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
                         int32_t cin, const void* packed, const float* bias, int32_t cout, void* y, int32_t y_ld,
                         int32_t y_coff, nc_stream_t stream) {

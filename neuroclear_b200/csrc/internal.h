@@ -129,6 +129,16 @@ int loss_fwd(const float* p, const float* q, float target, long long n, int mode
 int loss_bwd(const float* p, const float* q, float target, long long n, int mode, const float* upstream, float* dp,
              cudaStream_t stream);
 
+// patchgan.cu
+long long patchgan_ws_floats(int N, int H, int W, int ndf, int n_layers);
+int patchgan_fwd(const float* x, int N, int H, int W, int ndf, int n_layers, const float* const* weights,
+                 const float* const* biases, float* ws, float* pred, cudaStream_t stream);
+int patchgan_bwd(const float* x, const float* dpred, int N, int H, int W, int ndf, int n_layers,
+                 const float* const* weights, float* ws, float* dx, float* const* dweights, float* const* dbiases,
+                 cudaStream_t stream);
+int adam_step_multi(const void* table, int count, float lr, float beta1, float beta2, float eps, int step,
+                    cudaStream_t stream);
+
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
               int step, cudaStream_t stream);
 

@@ -119,6 +119,58 @@ class _Loss(torch.autograd.Function):
         return dp, (-dp if (q is not None and ctx.needs_input_grad[1]) else None), None, None
 
 
+class _PatchGANFn(torch.autograd.Function):
+    """The whole discriminator in one call per direction (nc_patchgan_fwd / nc_patchgan_bwd): the 18 passes of a
+    training iteration are launch-latency bound, so the layer loop lives inside the library, not in Python."""
+
+    @staticmethod
+    def forward(ctx, ndf, n_layers, x, *params):
+        import ctypes as C
+        from . import _lib
+        x = _check(x, "input")
+        n, cin, h, w = x.shape
+        if cin != 1:
+            raise NeuroclearError("the PatchGAN path takes 1-channel images")
+        ws_floats = _lib.load().nc_patchgan_ws_floats(n, h, w, ndf, n_layers)
+        if ws_floats < 0:
+            raise NeuroclearError(_lib.load().nc_last_error().decode())
+        L = n_layers + 2
+        ho, wo = h, w
+        for i in range(L):
+            s = 2 if i < n_layers else 1
+            ho, wo = (ho - 2) // s + 1, (wo - 2) // s + 1
+        params = [_check(p, "parameter") for p in params]
+        ws = torch.empty(ws_floats, dtype=torch.float32, device=x.device)
+        pred = torch.empty((n, 1, ho, wo), dtype=torch.float32, device=x.device)
+        wts = (C.c_void_p * L)(*[p.data_ptr() for p in params[0::2]])
+        bss = (C.c_void_p * L)(*[p.data_ptr() for p in params[1::2]])
+        with torch.cuda.device(x.device):
+            call("nc_patchgan_fwd", ptr(x), n, h, w, ndf, n_layers, wts, bss, ptr(ws), ptr(pred), stream_ptr())
+        ctx.save_for_backward(x, ws, *params)
+        ctx.meta = (ndf, n_layers)
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        import ctypes as C
+        x, ws, *params = ctx.saved_tensors
+        ndf, n_layers = ctx.meta
+        L = n_layers + 2
+        n, _, h, w = x.shape
+        dpred = dpred.contiguous()
+        need_x = ctx.needs_input_grad[2]
+        need_p = any(ctx.needs_input_grad[3:])
+        dx = torch.empty_like(x) if need_x else None
+        grads = [torch.empty_like(p) for p in params] if need_p else [None] * len(params)
+        wts = (C.c_void_p * L)(*[p.data_ptr() for p in params[0::2]])
+        dws = (C.c_void_p * L)(*[g.data_ptr() for g in grads[0::2]]) if need_p else None
+        dbs = (C.c_void_p * L)(*[g.data_ptr() for g in grads[1::2]]) if need_p else None
+        with torch.cuda.device(x.device):
+            call("nc_patchgan_bwd", ptr(x), ptr(dpred), n, h, w, ndf, n_layers, wts, ptr(ws), ptr(dx), dws, dbs,
+                 stream_ptr())
+        return (None, None, dx) + tuple(grads)
+
+
 class NLayerDiscriminator(nn.Module):
     """reference networks.py:1009-1067 with dimension=2 and InstanceNorm (use_bias=True); forward/backward on
     the kernels above.  Layer plan: (conv s2 + LReLU), (conv s2, IN, LReLU) x (n_layers-1), (conv s1, IN, LReLU),
@@ -150,11 +202,16 @@ class NLayerDiscriminator(nn.Module):
         self._plan.append((len(seq), 1, None))
         seq += [nn.Conv2d(ndf * nf, 1, kw, 1, padw)]
         self.model = nn.Sequential(*seq)
+        self._ndf, self._n_layers, self._input_nc = ndf, n_layers, input_nc
+        #: False runs the network layer by layer through the per-layer autograd Functions (same kernels)
+        self.fused_pass = True
 
     def forward(self, input):
         if not input.is_cuda:
             raise NeuroclearError("NLayerDiscriminator (B200): input is on the CPU; there is no CPU fallback")
         x = input.float()
+        if self.fused_pass and self._input_nc == 1:
+            return _PatchGANFn.apply(self._ndf, self._n_layers, x, *self.parameters())
         for idx, stride, follow in self._plan:
             conv = self.model[idx]
             x = _Conv2dK4.apply(x, conv.weight, conv.bias, stride, LRELU_SLOPE if follow == "lrelu" else 1.0)
@@ -186,10 +243,11 @@ class GANLoss(nn.Module):
         self.register_buffer("real_label", torch.tensor(target_real_label))
         self.register_buffer("fake_label", torch.tensor(target_fake_label))
         self.gan_mode = gan_mode
+        # host copies: reading the (device-resident) buffers back would synchronise the stream on every loss call
+        self._labels = (float(target_fake_label), float(target_real_label))
 
     def forward(self, prediction, target_is_real):
-        label = float(self.real_label if target_is_real else self.fake_label)
-        return _Loss.apply(prediction, None, label, 0)
+        return _Loss.apply(prediction, None, self._labels[1 if target_is_real else 0], 0)
 
 
 class L1Loss(nn.Module):

@@ -59,6 +59,63 @@ def data_parallel_discriminator_step(rank, world, dev):
     return worst <= 2e-6
 
 
+def data_parallel_apollo_step(rank, world, dev):
+    """Full apollo iteration, data parallel (BASELINE.json configs[3]): every rank trains on its own crop, the
+    gradients of both optimisers are averaged with one all-reduce each, so all ranks must hold identical weights
+    afterwards and those weights must equal a single-process replay with averaged gradients."""
+    import io
+    from argparse import Namespace
+    from contextlib import redirect_stdout
+    from neuroclear_b200.apollo_model import AxialToLateralGANApolloModel
+    from oracle import deeplinear, discriminator as odisc, unet
+    opt = Namespace(isTrain=True, gpu_ids=[dev.index], gan_mode="lsgan", randomize_projection_depth=False,
+                    projection_depth=6, min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1,
+                    ngf=64, ndf=64, netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3,
+                    norm="instance", no_dropout=True, init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1,
+                    direction="AtoB", lambda_A=5.0)
+    names = ["D_A_axial", "D_A_lateral", "D_B_axial", "D_B_lateral"]
+
+    def make(distributed):
+        with redirect_stdout(io.StringIO()):
+            m = AxialToLateralGANApolloModel(opt, dev, distributed=distributed)
+        m.netG_A.module.load_state_dict(unet.random_state_dict(seed=41, bias_std=0.05))
+        m.netG_B.module.load_state_dict(deeplinear.random_state_dict(seed=42))
+        for i, n in enumerate(names):
+            getattr(m, "net" + n).module.load_state_dict(odisc.random_state_dict(seed=50 + i))
+        return m
+
+    crop = lambda r: torch.rand((1, 1, 24, 24, 24), generator=torch.Generator().manual_seed(200 + r))
+    dp = make(True)
+    np.random.seed(70 + rank)
+    dp.set_input({"A": crop(rank), "A_paths": "x"})
+    dp.optimize_parameters()
+    # single-process replay of the generator update: gradients of every rank's crop, averaged, one Adam step
+    sp = make(False)
+    params = sp.optimizer_G.params
+    acc = [torch.zeros_like(p) for p in params]
+    for r in range(world):
+        sp.optimizer_G.zero_grad()
+        np.random.seed(70 + r)
+        sp.set_input({"A": crop(r), "A_paths": "x"})
+        sp.forward()
+        sp.backward_G()
+        for a, p in zip(acc, params):
+            a += p.grad
+    for a, p in zip(acc, params):
+        p.grad = a / world
+    sp.optimizer_G.step()
+    worst = max((a.detach() - b.detach()).abs().max().item() for a, b in zip(dp.optimizer_G.params, params))
+    # all ranks hold the same generator weights
+    flat = torch.cat([p.detach().reshape(-1) for p in dp.optimizer_G.params])
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(lo, hi))
+    print("rank %d/%d data-parallel apollo step: generators vs single-process replay max |dparam| %.3g, "
+          "identical across ranks %s" % (rank, world, worst, same), flush=True)
+    return worst <= 2e-6 and same
+
+
 def main():
     from neuroclear_b200.pipeline import DicedInference
     from oracle import unet as ounet
@@ -82,6 +139,7 @@ def main():
               (rank, world, shape, z0, z1, same, pc), flush=True)
         ok = ok and same and pc
     ok = data_parallel_discriminator_step(rank, world, dev) and ok
+    ok = data_parallel_apollo_step(rank, world, dev) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
