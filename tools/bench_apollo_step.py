@@ -1,7 +1,9 @@
 """GPU timing of the full apollo training iteration (BASELINE.json configs[2]/[3]: train_onecube.py
 axial_to_lateral_gan_apollo, unet_deconv + deep_linear_gen + basic D, batch 1, randomized projection depth 10) on a
 random crop: set_input (H2D of the crop) + optimize_parameters(), CUDA events on the launching stream.
-Usage: python tools/bench_apollo_step.py [S=108] [iters=5]"""
+Usage: python tools/bench_apollo_step.py [S=108] [iters=5]
+       python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+              tools/bench_apollo_step.py S iters        (data parallel: one crop per GPU, gradients all-reduced)"""
 import io
 import json
 import os
@@ -23,16 +25,27 @@ opt = Namespace(isTrain=True, gpu_ids=[0], gan_mode="lsgan", randomize_projectio
                 min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1, ngf=64, ndf=64,
                 netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3, norm="instance",
                 no_dropout=True, init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1, direction="AtoB", lambda_A=5.0)
-torch.manual_seed(0)
-np.random.seed(0)
+import torch.distributed as dist  # noqa: E402
+
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+opt.gpu_ids = [local]
+torch.manual_seed(0)             # same initial weights on every rank
+np.random.seed(rank)
 with redirect_stdout(io.StringIO()):
-    m = AxialToLateralGANApolloModel(opt, "cuda", distributed=False)
+    m = AxialToLateralGANApolloModel(opt, "cuda:%d" % local, distributed=world > 1)
+torch.manual_seed(100 + rank)    # different crops
 crops = [torch.rand((1, 1, S, S, S)).pin_memory() for _ in range(3)]
 ev = lambda: torch.cuda.Event(enable_timing=True)
 times, launches = [], 0
 for i in range(iters + 3):
     e0, e1 = ev(), ev()
     n0 = _lib.LAUNCHES
+    if world > 1:
+        dist.barrier()
     e0.record()
     m.set_input({"A": crops[i % 3], "A_paths": "synthetic"})
     m.optimize_parameters()
@@ -42,9 +55,17 @@ for i in range(iters + 3):
     if i >= 3:
         times.append(e0.elapsed_time(e1))
 ms = sum(times) / len(times)
+if world > 1:
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
 flop = 3 * (unet_engine.FLOP_PER_VOXEL + deeplinear_engine.FLOP_PER_VOXEL) * S ** 3      # reference layer FLOPs, fwd + 2x bwd
 losses = m.get_current_losses()
-print(json.dumps({"crop": S, "ms_per_iter": round(ms, 3), "iters_per_s": round(1e3 / ms, 2), "launches": launches,
-                  "reference_flop_tflops": round(flop / ms / 1e9, 1),
+if rank == 0:
+  print(json.dumps({"crop": S, "n_gpus": world, "ms_per_iter": round(ms, 3),
+                  "crops_per_s": round(world * 1e3 / ms, 2), "launches": launches,
+                  "reference_flop_tflops": round(world * flop / ms / 1e9, 1),
                   "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
                   "finite": all(np.isfinite(v) for v in losses.values())}))
+if world > 1:
+    dist.destroy_process_group()
