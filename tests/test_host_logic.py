@@ -126,3 +126,38 @@ def test_sharding_plans_cover_everything():
                 j = np.where(j >= g.padded[0], 2 * (g.padded[0] - 1) - j, j)
                 j = j[j < size[0]]
                 assert j.size == 0 or (lo <= j.min() and j.max() < hi)
+
+
+def test_deep_linear_tail_fold_is_exact():
+    """deeplinear_engine.fold_tail: the k3 layer followed by the three 1x1 layers == ONE 64->1 k3 stencil, borders
+    included (only pointwise ops follow the k3 layer), checked against the layered evaluation on the CPU."""
+    import torch.nn.functional as F
+    from neuroclear_b200.deeplinear_engine import FLOP_PER_VOXEL, KEYS, SHAPES, fold_tail
+    from oracle import deeplinear
+    assert SHAPES == deeplinear.STATE_DICT_SHAPES and tuple(KEYS) == tuple(deeplinear.STATE_DICT_SHAPES)
+    assert FLOP_PER_VOXEL * 108 ** 3 == pytest.approx(1630.4e9, rel=1e-3)          # SURVEY.md §2c
+    sd = deeplinear.random_state_dict(seed=1)
+    g = torch.Generator().manual_seed(2)
+    h2 = torch.randn((2, 64, 5, 6, 7), generator=g)
+    layered = h2
+    for k in KEYS[2:]:
+        layered = F.conv3d(layered, sd[k], padding=1 if sd[k].shape[-1] == 3 else 0)
+    K = fold_tail(*[sd[k] for k in KEYS[2:]])
+    assert tuple(K.shape) == (64, 27)
+    folded = F.conv3d(h2, K.reshape(1, 64, 3, 3, 3), padding=1)
+    assert float((folded - layered).abs().max()) <= 1e-5 * float(layered.abs().max())
+
+
+def test_generator_modules_keep_the_reference_state_dicts():
+    import io
+    from contextlib import redirect_stdout
+    from neuroclear_b200 import networks
+    from oracle import deeplinear
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "deep_linear_gen", "instance", False, "kaiming", 0.02, [], dimension=3)
+    sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == deeplinear.STATE_DICT_SHAPES
+    assert sum(p.numel() for p in net.parameters()) == deeplinear.N_PARAMS
+    net.load_state_dict(deeplinear.random_state_dict(0))
+    with pytest.raises(Exception):                      # CPU tensors: no fallback
+        net(torch.zeros((1, 1, 8, 8, 8)))
