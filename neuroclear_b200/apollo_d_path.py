@@ -24,52 +24,78 @@ from ._lib import call, f32, i64, ptr, stream_ptr
 from .projection import Volume
 
 
-class FusedAdam:
-    """torch.optim.Adam(params, lr, betas) semantics (no weight decay / amsgrad) on nc_adam_step."""
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr, betas) semantics (no weight decay / amsgrad) with ONE kernel launch per parameter
+    group (nc_adam_step_multi).  A real torch Optimizer: param_groups / state / zero_grad / state_dict and the
+    torch.optim.lr_scheduler classes (networks.get_scheduler) work as with the reference's torch.optim.Adam."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        self.params = [p for p in params]
-        self.lr, self.betas, self.eps = lr, betas, eps
-        self.state = {}
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
         self.step_count = 0
         self._table = None
         self._table_event = None
 
-    def zero_grad(self):
-        for p in self.params:
-            p.grad = None
+    @property
+    def params(self):
+        return [p for g in self.param_groups for p in g["params"]]
+
+    def _launch(self, table_dev, offset, count, group, step):
+        """one launch over `count` entries of the device table starting at entry `offset`"""
+        import ctypes as C
+        call("nc_adam_step_multi", C.c_void_p(table_dev.data_ptr() + 40 * offset), count, f32(group["lr"]),
+             f32(group["betas"][0]), f32(group["betas"][1]), f32(group["eps"]), step, stream_ptr())
 
     @torch.no_grad()
-    def step(self):
-        """One launch for all tensors: a pinned host table of {p, g, m, v, n} goes to the device asynchronously."""
+    def step(self, closure=None):
         import numpy as np
         self.step_count += 1
         if self._table_event is not None:
-            self._table_event.synchronize()
-        live = [p for p in self.params if p.grad is not None]
-        if not live:
+            self._table_event.synchronize()      # the pinned table of the previous step has been consumed
+        rows, spans, keep = [], [], []
+        for group in self.param_groups:
+            by_step = {}      # torch.optim.Adam counts steps PER PARAMETER (one skipped for lack of a gradient lags)
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"], st["exp_avg"], st["exp_avg_sq"] = 0, torch.zeros_like(p), torch.zeros_like(p)
+                st["step"] += 1
+                g = p.grad.contiguous()
+                keep.append(g)
+                by_step.setdefault(st["step"], []).append(
+                    [p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()])
+            for step, entries in sorted(by_step.items()):
+                spans.append((len(rows), len(entries), group, step))
+                rows += entries
+        if not rows:
             return
-        dev = live[0].device
-        grads = []
-        for p in live:
-            if p not in self.state:
-                self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
-            grads.append(p.grad.contiguous())
-        if self._table is None or self._table.shape[0] < len(live):
-            self._table = torch.empty((len(live), 5), dtype=torch.int64).pin_memory()
-        tab = self._table[:len(live)]
-        tab.numpy()[:] = np.array([[p.data_ptr(), g.data_ptr(), self.state[p][0].data_ptr(),
-                                    self.state[p][1].data_ptr(), p.numel()] for p, g in zip(live, grads)],
-                                  dtype=np.int64)
-        with torch.cuda.device(dev):
+        dev = self.param_groups[0]["params"][0].device
+        if self._table is None or self._table.shape[0] < len(rows):
+            self._table = torch.empty((len(rows), 5), dtype=torch.int64)
+            if dev.type == "cuda":
+                self._table = self._table.pin_memory()
+        tab = self._table[:len(rows)]
+        tab.numpy()[:] = np.array(rows, dtype=np.int64)
+        with torch.cuda.device(dev) if dev.type == "cuda" else _nullcontext():
             tab_dev = tab.to(dev, non_blocking=True)
-            call("nc_adam_step_multi", ptr(tab_dev), len(live), f32(self.lr), f32(self.betas[0]), f32(self.betas[1]),
-                 f32(self.eps), self.step_count, stream_ptr())
-            # the pinned table may be rewritten by the next step only after this copy has been consumed
-            self._table_event = torch.cuda.Event()
-            self._table_event.record()
-        for p in live:   # the kernel wrote through raw pointers: bump the version counters (autograd, weight caches)
-            torch.autograd.graph.increment_version(p)
+            for first, count, group, step in spans:
+                self._launch(tab_dev, first, count, group, step)
+            if dev.type == "cuda":
+                self._table_event = torch.cuda.Event()
+                self._table_event.record()
+        for group in self.param_groups:   # the kernel wrote through raw pointers: bump the version counters
+            for p in group["params"]:
+                if p.grad is not None:
+                    torch.autograd.graph.increment_version(p)
+
+
+class _nullcontext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def allreduce_mean_gradients(params, group=None):

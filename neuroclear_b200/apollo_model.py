@@ -12,12 +12,37 @@ SURVEY.md §8e)."""
 from __future__ import annotations
 
 import itertools
+import os
 from collections import OrderedDict
 
 import torch
 
 from . import networks
 from .apollo_d_path import ApolloDiscriminatorPath, FusedAdam, allreduce_mean_gradients
+
+def _unwrap(net):
+    return net.module if isinstance(net, torch.nn.DataParallel) else net
+
+
+def save_networks(nets, save_dir, epoch):
+    """base_model.py:146-162: '<epoch>_net_<name>.pth' holding the CPU state_dict of the unwrapped module (the
+    reference moves the module to the CPU and back; copying the tensors gives the same file)."""
+    os.makedirs(save_dir, exist_ok=True)
+    for name, net in nets.items():
+        sd = {k: v.detach().cpu() for k, v in _unwrap(net).state_dict().items()}
+        torch.save(sd, os.path.join(save_dir, "%s_net_%s.pth" % (epoch, name)))
+
+
+def load_networks(nets, save_dir, epoch, device="cpu"):
+    """base_model.py:178-201 (the InstanceNorm key patching there concerns checkpoints older than PyTorch 0.4)."""
+    for name, net in nets.items():
+        path = os.path.join(save_dir, "%s_net_%s.pth" % (epoch, name))
+        print("loading the model from %s" % path)
+        sd = torch.load(path, map_location=str(device))
+        if hasattr(sd, "_metadata"):
+            del sd._metadata
+        _unwrap(net).load_state_dict(sd)
+
 
 LOSS_NAMES = ["D_A_lateral", "D_A_axial", "G_A", "G_A_lateral", "G_A_axial", "cycle",
               "D_B_lateral", "D_B_axial", "G_B", "G_B_lateral", "G_B_axial"]      # apollo_model.py:61-62
@@ -44,6 +69,41 @@ class AxialToLateralGANApolloModel:
                                      lr=opt.lr, betas=(opt.beta1, 0.999))                        # :131-132
         self.optimizer_D = self.dpath.optimizer_D
         self.optimizers = [self.optimizer_G, self.optimizer_D]
+        self.model_names = ["G_A", "G_B", "D_A_lateral", "D_A_axial", "D_B_lateral", "D_B_axial"]     # :85
+        self.visual_names = ["real", "fake", "rec"]
+        self.schedulers = []
+        self.metric = 0
+        self.save_dir = os.path.join(getattr(opt, "checkpoints_dir", "./checkpoints"), getattr(opt, "name", "apollo"))
+
+    # ---- BaseModel protocol used by train_onecube.py (models/base_model.py:81-136,146-201)
+    def setup(self, opt):
+        self.schedulers = [networks.get_scheduler(o, opt) for o in self.optimizers]
+        if getattr(opt, "continue_train", False):
+            suffix = "iter_%d" % opt.load_iter if getattr(opt, "load_iter", 0) > 0 else opt.epoch
+            self.load_networks(suffix)
+
+    def update_learning_rate(self):
+        for sch in self.schedulers:
+            if getattr(self.opt, "lr_policy", "constant") == "plateau":
+                sch.step(self.metric)
+            else:
+                sch.step()
+
+    def eval(self):
+        for name in self.model_names:
+            getattr(self, "net" + name).eval()
+
+    def compute_visuals(self):
+        pass
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    def save_networks(self, epoch):
+        save_networks({n: getattr(self, "net" + n) for n in self.model_names}, self.save_dir, epoch)
+
+    def load_networks(self, epoch):
+        load_networks({n: getattr(self, "net" + n) for n in self.model_names}, self.save_dir, epoch, self.device)
 
     # ---- :142-160
     def set_input(self, input):

@@ -36,6 +36,25 @@ def get_norm_layer(norm_type="instance", dimension=3):
     raise NotImplementedError("normalization layer [%s] is not found" % norm_type)
 
 
+def get_scheduler(optimizer, opt):
+    """reference networks.py:50-86: linear | constant | step | plateau | cosine on the torch schedulers (host logic;
+    the optimisers of this package are torch Optimizers, see apollo_d_path.FusedAdam)."""
+    from torch.optim import lr_scheduler
+    if opt.lr_policy == "linear":
+        def lambda_rule(epoch):
+            return 1.0 - max(0, epoch + opt.epoch_count - opt.n_epochs) / float(opt.n_epochs_decay + 1)
+        return lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda_rule)
+    if opt.lr_policy == "constant":
+        return lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda epoch: 1.0)
+    if opt.lr_policy == "step":
+        return lr_scheduler.StepLR(optimizer, step_size=opt.lr_decay_iters, gamma=0.1)
+    if opt.lr_policy == "plateau":
+        return lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=0.2, threshold=0.01, patience=5)
+    if opt.lr_policy == "cosine":
+        return lr_scheduler.CosineAnnealingLR(optimizer, T_max=opt.n_epochs, eta_min=0)
+    raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+
+
 def init_weights(net, init_type="normal", init_gain=0.02):
     """reference networks.py:88-119 (same class-name matching, same initialisers)."""
     def init_func(m):

@@ -161,3 +161,72 @@ def test_generator_modules_keep_the_reference_state_dicts():
     net.load_state_dict(deeplinear.random_state_dict(0))
     with pytest.raises(Exception):                      # CPU tensors: no fallback
         net(torch.zeros((1, 1, 8, 8, 8)))
+
+
+def test_fused_adam_is_a_torch_optimizer_with_adam_semantics():
+    """FusedAdam's host logic (param groups, state, pointer table, version bump, lr schedulers) with the kernel
+    launch replaced by the same arithmetic on host memory: must track torch.optim.Adam step for step."""
+    import ctypes as C
+    from argparse import Namespace
+    from neuroclear_b200 import networks
+    from neuroclear_b200.apollo_d_path import FusedAdam
+
+    class HostAdam(FusedAdam):
+        def _launch(self, table, offset, count, group, step):
+            b1, b2 = group["betas"]
+            bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+            for p_, g_, m_, v_, n in table[offset:offset + count].tolist():
+                arr = lambda a: np.ctypeslib.as_array((C.c_float * n).from_address(a))
+                p, g, m, v = arr(p_), arr(g_), arr(m_), arr(v_)
+                m[:] = b1 * m + (1 - b1) * g
+                v[:] = b2 * v + (1 - b2) * g * g
+                p -= (group["lr"] / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + group["eps"])
+
+    g = torch.Generator().manual_seed(0)
+    init = [torch.randn(s, generator=g) for s in [(7, 3), (5,), (2, 2, 2)]]
+    mine = [torch.nn.Parameter(t.clone()) for t in init]
+    ref = [torch.nn.Parameter(t.clone()) for t in init]
+    o_mine = HostAdam([{"params": mine[:2]}, {"params": mine[2:], "lr": 3e-3}], lr=1e-2, betas=(0.1, 0.999))
+    o_ref = torch.optim.Adam([{"params": ref[:2]}, {"params": ref[2:], "lr": 3e-3}], lr=1e-2, betas=(0.1, 0.999))
+    opt = Namespace(lr_policy="linear", epoch_count=1, n_epochs=1, n_epochs_decay=3)
+    s_mine, s_ref = networks.get_scheduler(o_mine, opt), networks.get_scheduler(o_ref, opt)
+    assert o_mine.params == mine
+    for it in range(4):
+        for a, b in zip(mine, ref):
+            grad = torch.randn(a.shape, generator=g)
+            a.grad, b.grad = grad.clone(), grad.clone()
+        if it == 2:
+            mine[1].grad = ref[1].grad = None                      # parameters without gradient are skipped
+        v0 = mine[0]._version
+        o_mine.step()
+        o_ref.step()
+        assert mine[0]._version > v0                                # weight caches / autograd see the update
+        s_mine.step()
+        s_ref.step()
+        assert [gr["lr"] for gr in o_mine.param_groups] == [gr["lr"] for gr in o_ref.param_groups]
+        for a, b in zip(mine, ref):
+            assert float((a - b).abs().max()) <= 1e-6
+    o_mine.zero_grad()
+    assert all(p.grad is None for p in mine)
+    for policy, kw in (("constant", {}), ("step", {"lr_decay_iters": 2}), ("cosine", {"n_epochs": 5})):
+        networks.get_scheduler(o_mine, Namespace(lr_policy=policy, **kw)).step()
+    with pytest.raises(NotImplementedError):
+        networks.get_scheduler(o_mine, Namespace(lr_policy="nope"))
+
+
+def test_save_and_load_networks_round_trip(tmp_path):
+    """'<epoch>_net_<name>.pth' files as BaseModel.save_networks writes them (base_model.py:146-201)"""
+    import io
+    from contextlib import redirect_stdout
+    from neuroclear_b200 import networks
+    from neuroclear_b200.apollo_model import load_networks, save_networks
+    from oracle import deeplinear
+    with redirect_stdout(io.StringIO()):
+        a = networks.define_G(1, 1, 64, "deep_linear_gen", "instance", False, "kaiming", 0.02, [], dimension=3)
+        b = networks.define_G(1, 1, 64, "deep_linear_gen", "instance", False, "kaiming", 0.02, [], dimension=3)
+    a.load_state_dict(deeplinear.random_state_dict(5))
+    save_networks({"G_B": torch.nn.DataParallel(a) if False else a}, str(tmp_path), "latest")
+    assert (tmp_path / "latest_net_G_B.pth").exists()
+    with redirect_stdout(io.StringIO()):
+        load_networks({"G_B": b}, str(tmp_path), "latest")
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
