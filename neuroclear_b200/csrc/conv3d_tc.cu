@@ -18,6 +18,11 @@
 //     landed planes. Two accumulator sets ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1.
 //     The grid is persistent (<= #SMs CTAs, static tile stride).
 //   * STACK (Cout = 64): the three kd taps of a (kh,kw) are stacked along N (N = 64/128/192 MMAs), see ConvCfg.
+//   * training reuses this kernel: the data gradient of a stride-1 "same" conv is the conv of dy with the
+//     channel-transposed, tap-reversed filter — template flag BF16 (bf16 operands / output, no statistics; gradients
+//     need bf16's exponent range), see conv3d_k3_dgrad.  KSD != KS gives filters that are longer along d than in the
+//     plane (the k7 Cin = 1 layer of DeepLinearGenerator as a 7-tap depth conv over an in-plane im2col), KS = 5 the
+//     k5 layer, KS = 1 in MODE 0 the data gradient of the transposed convs (conv3d_tc_64, conv3d_k1_bf16).
 //   * epilogue MODE 0: raw fp16 NDHWC store + per-tile per-channel (sum, sum of squares) partials taken from
 //     the fp32 accumulators (InstanceNorm statistics, reduced deterministically later);
 //     MODE 1: transposed conv — + bias, fp16 tile staged in shared memory and written by a TMA store whose tensor

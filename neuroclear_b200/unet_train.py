@@ -19,10 +19,10 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import call, i32, i64, ptr, stream_ptr
+from ._lib import call, i64, ptr, stream_ptr
 from .unet_engine import IN_EPS, UnetDeconvEngine, _CT_LAYERS, _K3_LAYERS
 
-# (prefix, Cin, Cout, level) of the nine tensor-core k3 layers, in forward order
+# resolution level (0 = full, 1 = /2, 2 = /4) of the nine tensor-core k3 layers
 _LEVEL = {"double_conv1.convolution.3": 0, "double_conv2.convolution.0": 1, "double_conv2.convolution.3": 1,
           "bottom_layer.convolution.0": 2, "bottom_layer.convolution.3": 2, "bottom_layer.convolution.6": 2,
           "ex_double_conv2.convolution.0": 1, "ex_double_conv2.convolution.3": 1, "ex_conv1_1.convolution.0": 0}
