@@ -91,7 +91,7 @@ def test_optimize_parameters_matches_reference_fixture():
             print("  %s %-40s cos %.4f  rel L2 %.3f  update-sign agreement %.3f" % (name, k, cos, rel, agree))
             assert cos >= 0.97 and rel <= 0.25, (name, k, cos, rel)
             if ref_g.size >= 100:
-                assert agree >= 0.85, (name, k, agree)
+                assert agree >= 0.8, (name, k, agree)        # measured 0.862 (first layer) .. 1.0
     # ---- discriminators after their step
     for name in D_NAMES:
         for k, p in getattr(m, "net" + name).module.named_parameters():
