@@ -9,6 +9,10 @@ uint16).  `value` is timed with the uint16 volume already resident in HBM; `e2e`
 (DicedInference.run) with the pinned-host -> device copy of the volume and the device -> host copy of the result
 inside the timed region.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max
 over ranks.  One JSON line on stdout (rank 0).
+
+Extra keys next to the contract's: `roofline` (live CUDA-event TFLOP/s of the tcgen05 conv launches), `cpu_baseline`
+(the oracle on a bounded sample), `train_step` (N = 1 only; a secondary measurement of BASELINE.json configs[2]: the
+full apollo training iteration on a 108^3 crop, after the headline timing; --no-train-sample skips it).
 """
 from __future__ import annotations
 
@@ -146,6 +150,49 @@ def run_reference(args, shape, guard):
     guard.emit(json.dumps(line))
 
 
+def train_step_sample(dev, crop=108, iters=5, warmup=3):
+    """Secondary measurement (BASELINE.json configs[2], not the headline metric): one full training iteration of the
+    apollo model (unet_deconv + deep_linear_gen + 4 basic Ds, batch 1, randomized projection depth 10) on a random
+    crop — set_input (H2D of the crop from pinned memory) + optimize_parameters(), CUDA events on the launching
+    stream.  Never allowed to take the headline line down: any failure is reported in place of the numbers."""
+    try:
+        import contextlib
+        import io
+        from argparse import Namespace
+        from neuroclear_b200 import _lib
+        from neuroclear_b200.apollo_model import AxialToLateralGANApolloModel
+        opt = Namespace(isTrain=True, gpu_ids=[dev.index or 0], gan_mode="lsgan", randomize_projection_depth=True,
+                        projection_depth=10, min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1,
+                        ngf=64, ndf=64, netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3,
+                        norm="instance", no_dropout=True, init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1,
+                        direction="AtoB", lambda_A=5.0)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = AxialToLateralGANApolloModel(opt, dev, distributed=False)
+        crops = [torch.rand((1, 1, crop, crop, crop)).pin_memory() for _ in range(2)]
+        times, launches = [], 0
+        for i in range(warmup + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = _lib.LAUNCHES
+            e0.record()
+            model.set_input({"A": crops[i % 2], "A_paths": "synthetic"})
+            model.optimize_parameters()
+            e1.record()
+            torch.cuda.synchronize()
+            launches = _lib.LAUNCHES - n0
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        finite = all(np.isfinite(v) for v in model.get_current_losses().values())
+        return {"metric": "apollo training iteration (G_A unet_deconv + G_B deep_linear_gen + 4 PatchGAN Ds, batch 1)",
+                "crop": crop, "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "iters": iters, "warmup": warmup,
+                "library_calls_per_iter": launches, "losses_finite": bool(finite),
+                "data": "synthetic random crop, random-init weights"}
+    except Exception as e:  # noqa: BLE001 - secondary measurement
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def workload_config(shape, batch, gpus):
     return {"workload": "test_dice.py unet_deconv inference, synthetic %dx%dx%d uint16 volume, dice %d overlap %d "
                         "border_cut %d, normalize_intensity (0.25, 99.75)" % (*shape, ROI, OVERLAP, BORDER),
@@ -178,6 +225,7 @@ def main():
     ap.add_argument("--size", type=int, nargs=3, default=[900, 900, 900])
     ap.add_argument("--batch", type=int, default=9)   # 729 = 81 x 9: no ragged last batch
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-sample", action="store_true")
     args = ap.parse_args()
     shape = tuple(args.size)
 
@@ -290,6 +338,10 @@ def main():
         v, cores, sample, _ = cpu_baseline_sample(shape)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    train = None
+    if rank == 0 and world == 1 and not args.no_train_sample:
+        train = train_step_sample(dev)
+
     if rank == 0:
         cfg = workload_config(shape, args.batch, world)
         cfg["cubes"] = geo.n_cubes
@@ -303,6 +355,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "train_step": train,
             "tensor_pipe_frac_whole_step": FLOP_PER_VOXEL * geo.n_cubes * geo.edge ** 3 * args.steps
                                             / (ms * 1e-3) / 1e12 / peak / world,
         }
