@@ -288,6 +288,15 @@ int nc_loss_bwd(const float* p, const float* q, float target, int64_t n, int32_t
  * parameter tensor: p, exp_avg m, exp_avg_sq v updated in place from gradient g; `step` counts from 1. */
 int nc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  int32_t step, nc_stream_t stream);
+/* Training-data augmentation on the device (data/base_dataset.py:87-131, README --preprocess
+ * random3Drotate_randomcrop_randomflip_...): the rotated (cv2.warpAffine INTER_LINEAR, bit-exact), cropped, normalised
+ * and flipped float32 crop (cz,cy,cx), evaluated only at the crop's voxels from the uint16 volume (Z,H,W) in HBM.
+ * x0 / y0 (cy entries) and adelta / bdelta (cx entries): the inverse affine map in 1/1024 fixed point for the crop's
+ * destination rows / columns, computed by the host (neuroclear_b200/augment.py); flip_mask bits 0/1/2 = z/y/x. */
+int nc_augment_crop_u16(const uint16_t* vol, int32_t z, int32_t h, int32_t w, int32_t z0, int32_t cz, int32_t cy,
+                        int32_t cx, const int32_t* x0, const int32_t* y0, const int32_t* adelta, const int32_t* bdelta,
+                        int32_t flip_mask, float* out, nc_stream_t stream);
+
 /* All parameter tensors of one optimiser in a single launch.  table: DEVICE array of `count` entries
  * { float* p; const float* g; float* m; float* v; int64_t n; } (40 bytes each); same arithmetic as nc_adam_step. */
 int nc_adam_step_multi(const void* table, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "nc_conv3d_tc_64": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
     "nc_stencil64to1_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
     "nc_stencil64to1_bwd_data": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+    "nc_augment_crop_u16": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
     "nc_adam_step_multi": (C.c_int, [vp, i32, f32, f32, f32, f32, i32, vp]),
     "nc_patchgan_ws_floats": (i64, [i32, i32, i32, i32, i32]),
     "nc_patchgan_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),

@@ -173,6 +173,11 @@ int nc_adam_step_multi(const void* table, int32_t count, float lr, float beta1, 
                        nc_stream_t stream) {
   return adam_step_multi(table, count, lr, beta1, beta2, eps, step, S(stream));
 }
+int nc_augment_crop_u16(const uint16_t* vol, int32_t z, int32_t h, int32_t w, int32_t z0, int32_t cz, int32_t cy,
+                        int32_t cx, const int32_t* x0, const int32_t* y0, const int32_t* adelta, const int32_t* bdelta,
+                        int32_t flip_mask, float* out, nc_stream_t stream) {
+  return augment_crop_u16(vol, z, h, w, z0, cz, cy, cx, x0, y0, adelta, bdelta, flip_mask, out, S(stream));
+}
 int nc_convT3d_k2s2_fwd(const void* x, const float* in_mean_rstd, int32_t nb, int32_t d, int32_t h, int32_t w,
                         int32_t cin, const void* packed, const float* bias, int32_t cout, void* y, int32_t y_ld,
                         int32_t y_coff, nc_stream_t stream) {

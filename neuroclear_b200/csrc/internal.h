@@ -129,6 +129,10 @@ int loss_fwd(const float* p, const float* q, float target, long long n, int mode
 int loss_bwd(const float* p, const float* q, float target, long long n, int mode, const float* upstream, float* dp,
              cudaStream_t stream);
 
+// augment.cu
+int augment_crop_u16(const uint16_t* vol, int Z, int H, int W, int z0, int cz, int cy, int cx, const int* x0,
+                     const int* y0, const int* adelta, const int* bdelta, int flip_mask, float* out,
+                     cudaStream_t stream);
 // patchgan.cu
 long long patchgan_ws_floats(int N, int H, int W, int ndf, int n_layers);
 int patchgan_fwd(const float* x, int N, int H, int W, int ndf, int n_layers, const float* const* weights,

@@ -336,6 +336,59 @@ def golden_apollo_step():
     np.savez_compressed(os.path.join(GOLD, "apollo_step_32.npz"), **out)
 
 
+def golden_augment():
+    """The reference's training transform (data/base_dataset.py:87-131, README --preprocess
+    random3Drotate_randomcrop_randomflip_addColorChannel_addBatchChannel) with FIXED params (angle_3D, crop_pos,
+    flip_axis — get_transform's `params` path) on a 20x48x56 uint16 volume, for seven angles; asserts
+    oracle.augment.augment_crop (which only evaluates the crop) == reference (which rotates the whole volume),
+    and oracle.augment.warp_affine_u16 == cv2.warpAffine, bit for bit."""
+    rh.install()
+    import cv2
+    from argparse import Namespace
+    from data.base_dataset import get_transform
+    from oracle import augment
+    rng = np.random.default_rng(7)
+    vol = (rng.random((20, 48, 56)) ** 3 * 65535).astype(np.uint16)
+    out = {"vol": vol}
+    cases = []
+    for i, angle in enumerate([0, 7, 45, 90, 133, 212, 359]):
+        shape = augment.rotated_volume_shape(vol.shape, angle)
+        crop = (12, min(16, shape[1]), min(16, shape[2]))
+        pos = (int(rng.integers(0, 20 - crop[0] + 1)), int(rng.integers(0, shape[1] - crop[1] + 1)),
+               int(rng.integers(0, shape[2] - crop[2] + 1)))
+        flip = int(i % 3)
+        opt = Namespace(preprocess="random3Drotate_randomcrop_randomflip_addColorChannel_addBatchChannel",
+                        image_dimension=3, crop_size=list(crop))
+        ref = get_transform(opt, params={"angle_3D": angle, "crop_pos": pos, "flip_axis": flip})(vol)
+        got = augment.augment_crop(vol, angle, pos, crop, flip)
+        assert tuple(ref.shape) == got.shape == (1, 1) + crop, (angle, ref.shape, got.shape)
+        assert np.array_equal(ref.numpy(), got), angle
+        m, nw, nh = augment.rotate_plan(56, 48, angle)
+        full = cv2.warpAffine(vol[3], m, (nw, nh), flags=cv2.INTER_LINEAR)
+        assert np.array_equal(full, augment.warp_affine_u16(vol[3], m, np.arange(nw), np.arange(nh))), angle
+        cases.append([angle, *pos, *crop, flip])
+        out["crop_%d" % i] = ref.numpy()
+    out["cases"] = np.array(cases)
+    # the random path (params=None): same draws in the same order, seeded
+    import random
+    opt = Namespace(preprocess="random3Drotate_randomcrop_randomflip_addColorChannel_addBatchChannel",
+                    image_dimension=3, crop_size=[10, 12, 14])
+    tf = get_transform(opt)
+    drawn = []
+    for i, seed in enumerate([11, 12, 13, 14]):
+        random.seed(seed)
+        np.random.seed(seed)
+        ref = tf(vol)
+        random.seed(seed)
+        np.random.seed(seed)
+        got, (angle, pos, flips) = augment.random_item(vol, (10, 12, 14))
+        assert np.array_equal(ref.numpy(), got), (seed, angle, pos, flips)
+        out["random_%d" % i] = ref.numpy()
+        drawn.append([seed, angle, *pos, sum(1 << a for a in flips)])
+    out["random_cases"] = np.array(drawn)
+    np.savez_compressed(os.path.join(GOLD, "augment_20x48x56.npz"), **out)
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
@@ -349,6 +402,7 @@ def main():
     golden_discriminator()
     golden_apollo_discriminator_path()
     golden_apollo_step()
+    golden_augment()
     print("golden vectors written to", GOLD)
 
 
