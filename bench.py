@@ -150,7 +150,34 @@ def run_reference(args, shape, guard):
     guard.emit(json.dumps(line))
 
 
-def train_step_sample(dev, crop=108, iters=5, warmup=3):
+def train_step_cpu_baseline(sample_crop, crop):
+    """The oracle's restatement of the reference training iteration (oracle/apollo_step.py, torch CPU fp32 autograd,
+    pinned to the reference fixture) on the host cores, on a bounded sample: one iteration at sample_crop^3 after
+    one warm-up, scaled to `crop`^3 by the voxel ratio (the generators' cost is linear in the voxel count)."""
+    try:
+        from oracle import apollo_step, deeplinear, discriminator, unet
+        sds = {"G_A": unet.random_state_dict(seed=1), "G_B": deeplinear.random_state_dict(seed=2)}
+        for i, n in enumerate(apollo_step.D_NAMES):
+            sds[n] = discriminator.random_state_dict(seed=3 + i)
+        step = apollo_step.ApolloStep(sds)
+        np.random.seed(0)
+        g = torch.Generator().manual_seed(0)
+        ms = 0.0
+        for it in range(2):
+            step.set_input(torch.rand((1, 1, sample_crop, sample_crop, sample_crop), generator=g))
+            t0 = time.perf_counter()
+            step.optimize_parameters()
+            ms = (time.perf_counter() - t0) * 1e3
+        scaled = ms * (crop / sample_crop) ** 3
+        return {"value": 1e3 / scaled, "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
+                "ms_per_iter_sample": ms, "ms_per_iter_scaled": scaled,
+                "sample": "one optimize_parameters() of the oracle at %d^3, scaled to %d^3 by the voxel ratio"
+                          % (sample_crop, crop)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def train_step_sample(dev, crop=108, iters=5, warmup=3, cpu_crop=0):
     """Secondary measurement (BASELINE.json configs[2], not the headline metric): one full training iteration of the
     apollo model (unet_deconv + deep_linear_gen + 4 basic Ds, batch 1, randomized projection depth 10) on a random
     crop — set_input (H2D of the crop from pinned memory) + optimize_parameters(), CUDA events on the launching
@@ -185,10 +212,13 @@ def train_step_sample(dev, crop=108, iters=5, warmup=3):
                 times.append(e0.elapsed_time(e1))
         ms = sum(times) / len(times)
         finite = all(np.isfinite(v) for v in model.get_current_losses().values())
-        return {"metric": "apollo training iteration (G_A unet_deconv + G_B deep_linear_gen + 4 PatchGAN Ds, batch 1)",
-                "crop": crop, "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "iters": iters, "warmup": warmup,
-                "library_calls_per_iter": launches, "losses_finite": bool(finite),
-                "data": "synthetic random crop, random-init weights"}
+        out = {"metric": "apollo training iteration (G_A unet_deconv + G_B deep_linear_gen + 4 PatchGAN Ds, batch 1)",
+               "crop": crop, "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "iters": iters, "warmup": warmup,
+               "library_calls_per_iter": launches, "losses_finite": bool(finite),
+               "data": "synthetic random crop, random-init weights"}
+        if cpu_crop:
+            out["cpu_baseline"] = train_step_cpu_baseline(cpu_crop, crop)
+        return out
     except Exception as e:  # noqa: BLE001 - secondary measurement
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
@@ -340,7 +370,7 @@ def main():
 
     train = None
     if rank == 0 and world == 1 and not args.no_train_sample:
-        train = train_step_sample(dev)
+        train = train_step_sample(dev, cpu_crop=0 if args.no_cpu_baseline else 48)
 
     if rank == 0:
         cfg = workload_config(shape, args.batch, world)

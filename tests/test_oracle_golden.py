@@ -143,3 +143,25 @@ def test_unet_gradient_oracle_matches_reference_fixture():
         ref = torch.from_numpy(z["gsample_" + k])
         got = grads[k].reshape(-1)[::61]
         assert float((got - ref).abs().max()) <= 1e-4 * max(float(z["gnorm_" + k][1]), 1e-7), k
+
+
+def test_apollo_step_oracle_matches_reference_fixture():
+    """oracle/apollo_step.py (the whole training iteration restated) vs one optimize_parameters() of the reference
+    model: identical losses, identical parameters of all six networks after both Adam updates."""
+    from oracle import apollo_step, deeplinear, discriminator
+    z = np.load(os.path.join(GOLDEN, "apollo_step_32.npz"))
+    sds = {"G_A": unet.random_state_dict(seed=21, bias_std=0.05), "G_B": deeplinear.random_state_dict(seed=22)}
+    for i, n in enumerate(apollo_step.D_NAMES):
+        sds[n] = discriminator.random_state_dict(seed=30 + i)
+    m = apollo_step.ApolloStep(sds)
+    np.random.seed(3)
+    m.set_input(torch.from_numpy(z["real"]))
+    losses = m.optimize_parameters()
+    assert m.depth == int(z["depth"])
+    for k, v in losses.items():
+        assert abs(v - float(z["loss_" + k])) <= 1e-6 * max(1.0, abs(v)), k
+    for n in ["G_A", "G_B"] + apollo_step.D_NAMES:
+        for k, t in m.p[n].items():
+            flat = t.detach().numpy().reshape(-1)
+            got = flat if flat.size <= 4096 else flat[::61]
+            assert np.abs(got - z["after_%s.%s" % (n, k)]).max() <= 1e-7, (n, k)
