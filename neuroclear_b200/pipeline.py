@@ -10,6 +10,8 @@ size because the blend always runs in ascending cube index on the slab owner.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -127,6 +129,30 @@ class DicedInference:
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return out_host.numpy(), plan["out_planes"]
+
+    def run_file(self, in_path, out_path):
+        """test_dice.py end to end on files: read the (multi-page, uncompressed) TIFF volume `in_path`, run the path,
+        write the result TIFF `out_path` (skimage.io.imread / tifffile.imsave in the reference, diceImage_dataset.py:35,
+        test_dice.py:151).  Sharded: every rank reads only the input planes it needs into pinned memory and writes
+        its own output slab into the shared file; rank 0 adds the header and the page directory."""
+        from . import volume_io
+        tv = volume_io.TiffVolume(in_path)
+        size = tv.shape
+        plan = self.plan(size)
+        z0, z1 = plan["in_planes"]
+        dt = torch.uint16 if tv.dtype.itemsize == 2 else torch.uint8
+        slab = torch.empty((z1 - z0,) + size[1:], dtype=dt).pin_memory()
+        tv.read(z0, z1, out=slab.numpy())
+        planes, (o0, o1) = self.run_slab(slab, z0, size)
+        layout = volume_io.TiffLayout(size, planes.dtype)
+        if self.rank == 0 and os.path.exists(out_path):
+            os.remove(out_path)
+        if self.world > 1:
+            dist.barrier(self.group)
+        volume_io.write_planes(out_path, layout, planes, o0, write_directory=self.rank == 0)
+        if self.world > 1:
+            dist.barrier(self.group)
+        return layout
 
     def run(self, volume, out_host: torch.Tensor = None):
         """volume: uint16 (Z,Y,X) numpy array or host tensor.  Returns (planes, (z_begin, z_end)): this rank's

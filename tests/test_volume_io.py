@@ -1,0 +1,100 @@
+"""neuroclear_b200.volume_io (TIFF / BigTIFF plane-range reader and shared-file writer) against Pillow's TIFF codec."""
+import os
+
+import numpy as np
+import pytest
+
+from neuroclear_b200 import volume_io as vio
+from neuroclear_b200._lib import NeuroclearError
+
+Image = pytest.importorskip("PIL.Image")
+
+
+def _volume(shape, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, np.iinfo(dtype).max + 1, shape).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
+def test_written_file_is_read_back_by_pillow(tmp_path, dtype):
+    vol = _volume((5, 13, 17), dtype)
+    path = str(tmp_path / "out.tif")
+    vio.write_volume(path, vol)
+    with Image.open(path) as im:
+        assert im.n_frames == 5
+        for z in range(5):
+            im.seek(z)
+            assert np.array_equal(np.array(im), vol[z]), z
+
+
+@pytest.mark.parametrize("dtype,mode", [(np.uint16, "I;16"), (np.uint8, "L")])
+def test_reads_pillow_multipage_files_and_plane_ranges(tmp_path, dtype, mode):
+    vol = _volume((6, 11, 9), dtype, seed=1)
+    path = str(tmp_path / "in.tif")
+    frames = [Image.fromarray(vol[z]) for z in range(6)]
+    frames[0].save(path, save_all=True, append_images=frames[1:])
+    tv = vio.TiffVolume(path)
+    assert tv.shape == (6, 11, 9) and tv.dtype == np.dtype(dtype)
+    assert np.array_equal(tv.read(), vol)
+    out = np.empty((3, 11, 9), dtype=dtype)
+    assert tv.read(2, 5, out=out) is out and np.array_equal(out, vol[2:5])
+    assert np.array_equal(vio.read_volume(path, 5, 6), vol[5:6])
+
+
+def test_bigtiff_round_trip_and_big_endian(tmp_path):
+    vol = _volume((4, 7, 5), np.uint16, seed=2)
+    path = str(tmp_path / "big.tif")
+    layout = vio.write_volume(path, vol, bigtiff=True)
+    assert layout.big and os.path.getsize(path) == layout.file_size
+    assert np.array_equal(vio.read_volume(path), vol)
+    # a big-endian classic file (as some microscopes write): build it by hand from the little-endian layout
+    le = vio.TiffLayout(vol.shape, vol.dtype, bigtiff=False)
+    head, ifds = le.directory_bytes()
+    import struct
+    be = bytearray(b"MM" + struct.pack(">HI", 42, le.ifd_offset))
+    be += vol.astype(">u2").tobytes()
+    for k in range(4):
+        nxt = le.ifd_offset + (k + 1) * le.ifd_size if k < 3 else 0
+        ent = [(256, 4, 5), (257, 4, 7), (258, 3, 16), (259, 3, 1), (262, 3, 1), (273, 4, le.plane_offset(k)),
+               (277, 3, 1), (278, 4, 7), (279, 4, le.plane)]
+        be += struct.pack(">H", len(ent))
+        for tag, typ, val in ent:
+            be += struct.pack(">HHI", tag, typ, 1) + (struct.pack(">HH", val, 0) if typ == 3 else struct.pack(">I", val))
+        be += struct.pack(">I", nxt)
+    p2 = str(tmp_path / "be.tif")
+    open(p2, "wb").write(bytes(be))
+    assert np.array_equal(vio.read_volume(p2), vol)
+
+
+def test_ranks_write_disjoint_slabs_of_one_file(tmp_path):
+    """the sharded pipeline: every rank writes its output z-slab at its final offset, rank 0 adds the directory"""
+    vol = _volume((9, 10, 12), np.uint16, seed=3)
+    path = str(tmp_path / "shared.tif")
+    layout = vio.TiffLayout(vol.shape, vol.dtype)
+    assert not layout.big
+    for z0, z1, first in ((6, 9, False), (0, 2, True), (2, 6, False)):      # any order
+        vio.write_planes(path, layout, vol[z0:z1], z0, write_directory=first)
+    assert os.path.getsize(path) == layout.file_size
+    assert np.array_equal(vio.read_volume(path), vol)
+    with Image.open(path) as im:
+        im.seek(7)
+        assert np.array_equal(np.array(im), vol[7])
+    assert vio.TiffLayout((1024, 2048, 2048), np.uint16).big            # config 5: 8.6 GB -> BigTIFF
+
+
+def test_error_behaviour(tmp_path):
+    vol = _volume((2, 8, 8), np.uint16)
+    path = str(tmp_path / "lzw.tif")
+    frames = [Image.fromarray(vol[z]) for z in range(2)]
+    frames[0].save(path, save_all=True, append_images=frames[1:], compression="tiff_lzw")
+    with pytest.raises(NeuroclearError):
+        vio.TiffVolume(path)
+    open(str(tmp_path / "junk.tif"), "wb").write(b"not a tiff at all")
+    with pytest.raises(NeuroclearError):
+        vio.TiffVolume(str(tmp_path / "junk.tif"))
+    good = str(tmp_path / "good.tif")
+    vio.write_volume(good, vol)
+    with pytest.raises(NeuroclearError):
+        vio.read_volume(good, 1, 5)
+    with pytest.raises(NeuroclearError):
+        vio.write_volume(good, vol.astype(np.float32))
