@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import discriminator
-from ._lib import call, f32, i64, ptr, stream_ptr
+from ._lib import call, f32, stream_ptr
 from .projection import Volume
 
 

@@ -10,7 +10,6 @@ containers only.  CUDA only: there is no CPU fallback.
 """
 from __future__ import annotations
 
-import functools
 
 import torch
 import torch.nn as nn

@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 from . import sharding
 from ._lib import NeuroclearError
-from .dicing import (DiceGeometry, PercentileSelect, blend_gather, dice_extract, dice_geometry, rescale_u16_crop)
+from .dicing import (PercentileSelect, blend_gather, dice_extract, dice_geometry, rescale_u16_crop)
 from .unet_engine import UnetDeconvEngine
 
 

@@ -28,7 +28,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import call, i32, i64, ptr, stream_ptr
+from ._lib import call, i64, ptr, stream_ptr
 
 IN_EPS = 1e-5  # torch.nn.InstanceNorm3d default, used by networks.get_norm_layer (networks.py:33-34)
 
