@@ -126,7 +126,9 @@ def rescale_u16_crop(vis: torch.Tensor, vis_z0: int, geo: DiceGeometry, norm3, z
 
 # ---------------------------------------------------------------------------------------------- dataset
 def _load_volume(path):
-    """Volume I/O is outside the hot path; .npy always works, TIFF stacks through cv2."""
+    """skimage.io.imread of the reference (diceImage_dataset.py:35): .npy, or a multi-page TIFF / BigTIFF through
+    neuroclear_b200.volume_io (uncompressed pages, read straight into one array); compressed or tiled TIFFs fall back
+    to cv2's codec."""
     if os.path.isdir(path):
         names = sorted(f for f in os.listdir(path) if not f.startswith(".") and
                        f.lower().endswith((".npy", ".tif", ".tiff")))
@@ -135,6 +137,11 @@ def _load_volume(path):
         path = os.path.join(path, names[0])
     if path.lower().endswith(".npy"):
         return np.load(path)
+    from . import volume_io
+    try:
+        return volume_io.read_volume(path)
+    except NeuroclearError:
+        pass
     import cv2
     ok, pages = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)
     if not ok:

@@ -98,3 +98,18 @@ def test_error_behaviour(tmp_path):
         vio.read_volume(good, 1, 5)
     with pytest.raises(NeuroclearError):
         vio.write_volume(good, vol.astype(np.float32))
+
+
+def test_dataset_loader_reads_tiff_directories(tmp_path):
+    """dicing._load_volume (the imread of DiceImageDataSet): first volume file of --dataroot, own reader for plain
+    TIFFs, cv2 fallback for compressed ones"""
+    from neuroclear_b200.dicing import _load_volume
+    vol = _volume((3, 9, 7), np.uint16, seed=5)
+    d = tmp_path / "data"
+    d.mkdir()
+    vio.write_volume(str(d / "a_volume.tif"), vol)
+    assert np.array_equal(_load_volume(str(d)), vol)
+    pytest.importorskip("cv2")
+    frames = [Image.fromarray(vol[z]) for z in range(3)]
+    frames[0].save(str(tmp_path / "lzw.tif"), save_all=True, append_images=frames[1:], compression="tiff_lzw")
+    assert np.array_equal(_load_volume(str(tmp_path / "lzw.tif")), vol)
