@@ -77,19 +77,14 @@ class ApolloStep:
         f = mip.get_slice(fake.detach(), ax_fake)[0]
         return self._backward_D(name, r, f)
 
-    def optimize_parameters(self):
+    def set_requires_grad_D(self, flag):
+        for n in D_NAMES:
+            for t in self.p[n].values():
+                t.requires_grad_(flag)
+
+    def backward_D(self):
+        """the four backward_D_* calls of optimize_parameters (:302-306), in order"""
         L = self.loss
-        self.forward()
-        for n in D_NAMES:
-            for t in self.p[n].values():
-                t.requires_grad_(False)
-        self.opt_G.zero_grad()
-        self.backward_G()
-        self.opt_G.step()
-        for n in D_NAMES:
-            for t in self.p[n].values():
-                t.requires_grad_(True)
-        self.opt_D.zero_grad()
         L["D_A_lateral"] = self._D_projection("D_A_lateral", self.real, self.fake, 0, 0)
         a1 = self._D_projection("D_A_axial", self.real, self.fake, 0, 1)
         a2 = self._D_projection("D_A_axial", self.real, self.fake, 0, 2)
@@ -98,5 +93,15 @@ class ApolloStep:
         b1 = self._D_slice("D_B_axial", self.real, self.rec, 1, 1)
         b2 = self._D_slice("D_B_axial", self.real, self.rec, 2, 2)
         L["D_B_axial"] = (b1 + b2) * 0.5
+
+    def optimize_parameters(self):
+        self.forward()
+        self.set_requires_grad_D(False)
+        self.opt_G.zero_grad()
+        self.backward_G()
+        self.opt_G.step()
+        self.set_requires_grad_D(True)
+        self.opt_D.zero_grad()
+        self.backward_D()
         self.opt_D.step()
-        return {k: float(v.detach()) for k, v in L.items()}
+        return {k: float(v.detach()) for k, v in self.loss.items()}

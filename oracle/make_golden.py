@@ -262,6 +262,7 @@ def golden_apollo_discriminator_path():
     gradients w.r.t. fake and rec — both with a fixed np.random seed, D weights from the oracle's seeded state dicts."""
     rh.install()
     from models.axial_to_lateral_gan_apollo_model import AxialToLateralGANApolloModel
+    torch.manual_seed(20211114)       # the generators keep their init_weights() draw (see main())
     with redirect_stdout(io.StringIO()):
         m = AxialToLateralGANApolloModel(apollo_opt())
     for i, name in enumerate(D_NAMES):
@@ -393,14 +394,20 @@ def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
     os.makedirs(GOLD, exist_ok=True)
+    # Every function seeds what it draws (torch Generators, np.random.seed, seeded state dicts), so the fixtures do not
+    # depend on the order of the calls.  One historical exception: the committed apollo_d_path_32.npz was recorded
+    # before golden_apollo_discriminator_path seeded torch's global RNG (the generators' init_weights() draw, i.e. its
+    # fake / rec volumes); re-running it writes different — equally valid — fake / rec volumes.  The fixture is
+    # self-contained (the tests read real / fake / rec from it), and tests/test_oracle_golden.py re-derives its
+    # losses and gradients with the oracle on every CPU run.
     golden_geometry()
     golden_dice_assemble()
     golden_unet()
-    golden_unet_grad()
-    golden_deeplinear()
     golden_mip()
     golden_discriminator()
     golden_apollo_discriminator_path()
+    golden_unet_grad()
+    golden_deeplinear()
     golden_apollo_step()
     golden_augment()
     print("golden vectors written to", GOLD)

@@ -165,3 +165,40 @@ def test_apollo_step_oracle_matches_reference_fixture():
             flat = t.detach().numpy().reshape(-1)
             got = flat if flat.size <= 4096 else flat[::61]
             assert np.abs(got - z["after_%s.%s" % (n, k)]).max() <= 1e-7, (n, k)
+
+
+def test_apollo_discriminator_path_oracle_matches_reference_fixture():
+    """oracle/apollo_step.py's generator-side losses (backward_G) and discriminator half against the fixture recorded
+    from the reference model on given real / fake / rec volumes (apollo_d_path_32.npz): losses, d loss / d fake,
+    d loss / d rec, discriminator gradients and Adam-updated weights."""
+    from oracle import apollo_step, deeplinear, discriminator
+    z = np.load(os.path.join(GOLDEN, "apollo_d_path_32.npz"))
+    sds = {"G_A": unet.random_state_dict(seed=0), "G_B": deeplinear.random_state_dict(seed=0)}      # unused here
+    for i, n in enumerate(apollo_step.D_NAMES):
+        sds[n] = discriminator.random_state_dict(seed=10 + i)
+    m = apollo_step.ApolloStep(sds)
+    m.real, m.depth = torch.from_numpy(z["real"]), int(z["depth"])
+    m.fake = torch.from_numpy(z["fake"]).requires_grad_(True)
+    m.rec = torch.from_numpy(z["rec"]).requires_grad_(True)
+    m.set_requires_grad_D(False)
+    np.random.seed(9)
+    m.backward_G()
+    for k in ("G_A", "G_A_lateral", "G_A_axial", "G_B", "G_B_lateral", "G_B_axial", "cycle"):
+        assert abs(float(m.loss[k]) - float(z["loss_" + k])) <= 1e-6, k
+    assert float((m.fake.grad - torch.from_numpy(z["dfake"])).abs().max()) <= 1e-9
+    assert float((m.rec.grad - torch.from_numpy(z["drec"])).abs().max()) <= 1e-9
+    m.set_requires_grad_D(True)
+    m.fake, m.rec = m.fake.detach(), m.rec.detach()
+    m.opt_D.zero_grad()
+    np.random.seed(7)
+    m.backward_D()
+    for k in ("D_A_lateral", "D_A_axial", "D_B_lateral", "D_B_axial"):
+        assert abs(float(m.loss[k]) - float(z["loss_" + k])) <= 1e-6, k
+    for n in apollo_step.D_NAMES:
+        for k, t in m.p[n].items():
+            ref = z["grad_%s.%s" % (n, k)]
+            assert np.abs(t.grad.numpy().reshape(-1)[::61] - ref).max() <= 1e-6 * (1 + np.abs(ref).max()), (n, k)
+    m.opt_D.step()
+    for n in apollo_step.D_NAMES:
+        for k, t in m.p[n].items():
+            assert np.abs(t.detach().numpy().reshape(-1)[::61] - z["after_%s.%s" % (n, k)]).max() <= 1e-7, (n, k)
