@@ -230,3 +230,26 @@ def test_save_and_load_networks_round_trip(tmp_path):
     with redirect_stdout(io.StringIO()):
         load_networks({"G_B": b}, str(tmp_path), "latest")
     assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the package (nor __graft_entry__.build) may import it, and in
+    bench.py only the cpu_baseline / --impl reference legs do."""
+    import ast
+    pkg = os.path.join(ROOT, "neuroclear_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            mods = [a.name for a in node.names] if isinstance(node, ast.Import) else \
+                [node.module or ""] if isinstance(node, ast.ImportFrom) else []
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), fn
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"cpu_baseline_sample", "run_reference", "train_step_cpu_baseline"}
+    for fdef in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fdef):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                assert fdef.name in allowed, fdef.name
+    for node in tree.body:                                              # nothing at module level
+        assert not (isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle")
