@@ -266,6 +266,30 @@ class Assemble_Dice:
         z, y, x = self.indexTo3DIndex(index)
         return z * self.step, y * self.step, x * self.step
 
+    # ---- flip test-time augmentation helpers (assemble_dice.py:79-128): pure tensor re-indexing + a 4-way mean,
+    # device-agnostic torch ops (not on the hot path; test_dice.py does not call them)
+    def varycubeinput(self, input):
+        """[input, input flipped along z, along y, along x] as dataset-style dicts"""
+        names = list(input.keys())
+        vol, path = input[names[0]], input[names[1]]
+        out = [input]
+        for axis in range(2, vol.dim()):
+            d = OrderedDict()
+            d[names[0]] = vol.flip(axis)
+            d[names[1]] = path
+            out.append(d)
+        return out
+
+    def combinecube(self, visual_list):
+        """un-flip the outputs of varycubeinput's copies and average them with the unflipped one"""
+        keys = list(visual_list[0].keys())
+        ndim = visual_list[0][keys[0]].dim()
+        out = OrderedDict()
+        for name in keys:
+            stack = [visual_list[0][name]] + [v[name].flip(2 + i) for i, v in enumerate(visual_list[1:ndim - 1])]
+            out[name] = torch.mean(torch.stack(stack, dim=0), dim=0)
+        return out
+
     def addToStack(self, cube):
         """cube: dict with 'real' and 'fake' (1,1,E,E,E) tensors, as BaseModel.get_current_visuals() returns."""
         bc = self.border_cut

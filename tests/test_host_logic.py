@@ -253,3 +253,22 @@ def test_product_never_imports_the_oracle():
                 assert fdef.name in allowed, fdef.name
     for node in tree.body:                                              # nothing at module level
         assert not (isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle")
+
+
+def test_flip_tta_helpers_match_the_reference_semantics():
+    """Assemble_Dice.varycubeinput / combinecube (assemble_dice.py:79-128): for a flip-equivariant 'network' the
+    combined result equals the plain one; for a general one it is the mean over the four un-flipped outputs."""
+    from collections import OrderedDict
+    from neuroclear_b200.dicing import Assemble_Dice
+    helper = Assemble_Dice.__new__(Assemble_Dice)           # the helpers use no instance state
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((1, 1, 4, 5, 6), generator=g)
+    copies = helper.varycubeinput(OrderedDict([("A", x), ("A_paths", "7")]))
+    assert len(copies) == 4 and all(c["A_paths"] == "7" for c in copies)
+    assert torch.equal(copies[0]["A"], x) and all(torch.equal(copies[1 + i]["A"], x.flip(2 + i)) for i in range(3))
+    w = torch.rand((1, 1, 4, 5, 6), generator=g)
+    net = lambda t: t * w                                    # not flip-equivariant
+    outs = [OrderedDict([("real", c["A"]), ("fake", net(c["A"]))]) for c in copies]
+    comb = helper.combinecube(outs)
+    want = (x * w + sum((x.flip(2 + i) * w).flip(2 + i) for i in range(3))) / 4
+    assert torch.allclose(comb["fake"], want) and torch.allclose(comb["real"], x)
