@@ -81,6 +81,17 @@ class AxialToLateralGANApolloModel:
         if getattr(opt, "continue_train", False):
             suffix = "iter_%d" % opt.load_iter if getattr(opt, "load_iter", 0) > 0 else opt.epoch
             self.load_networks(suffix)
+        self.print_networks(getattr(opt, "verbose", False))
+
+    def print_networks(self, verbose=False):
+        """base_model.py:203-219"""
+        print("---------- Networks initialized -------------")
+        for name in self.model_names:
+            net = getattr(self, "net" + name)
+            if verbose:
+                print(net)
+            print("[Network %s] Total number of parameters : %.3f M" % (name, sum(p.numel() for p in net.parameters()) / 1e6))
+        print("-----------------------------------------------")
 
     def update_learning_rate(self):
         for sch in self.schedulers:
