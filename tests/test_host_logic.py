@@ -272,3 +272,21 @@ def test_flip_tta_helpers_match_the_reference_semantics():
     comb = helper.combinecube(outs)
     want = (x * w + sum((x.flip(2 + i) * w).flip(2 + i) for i in range(3))) / 4
     assert torch.allclose(comb["fake"], want) and torch.allclose(comb["real"], x)
+
+
+def test_host_side_sizing_functions_of_the_training_abi(lib):
+    """pure host functions of the library (no launch): workspace / scratch sizing used by the training path"""
+    # PatchGAN workspace: conv outputs + IN outputs + statistics of the five layers + two gradient ping-pong buffers
+    n = lib.nc_patchgan_ws_floats(1, 108, 108, 64, 3)
+    sizes = [(64, 54), (128, 27), (256, 13), (512, 12), (1, 11)]
+    acts = [c * s * s for c, s in sizes]
+    want = sum(acts) + sum(acts[1:4]) + 2 * (128 + 256 + 512) + 2 * max(max(acts), 108 * 108)
+    assert n == want
+    assert lib.nc_patchgan_ws_floats(1, 16, 16, 64, 3) == -1 and b"too small" in lib.nc_last_error()
+    # weight-gradient split-K scratch: splits x taps x Cin x Cout floats, splits = #SMs / work items (148 without a GPU)
+    for ks, taps, groups in ((3, 27, 1), (5, 125, 2), (1, 1, 1), (71, 7, 1)):
+        items = 1 * 1 * (7 if ks == 71 else ks) * groups
+        b = lib.nc_conv3d_wgrad_scratch_bytes(ks, 1, 108, 108, 108, 64, 64)
+        assert b == (148 // items) * taps * 64 * 64 * 4, ks
+    assert lib.nc_conv3d_wgrad_scratch_bytes(3, 1, 2, 8, 8, 256, 256) == 2 * 27 * 256 * 256 * 4     # 2 plane tiles only
+    assert lib.nc_bwd_scratch_bytes(2) == 148 * 8 * 2 * 512 * 4
