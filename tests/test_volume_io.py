@@ -113,3 +113,26 @@ def test_dataset_loader_reads_tiff_directories(tmp_path):
     frames = [Image.fromarray(vol[z]) for z in range(3)]
     frames[0].save(str(tmp_path / "lzw.tif"), save_all=True, append_images=frames[1:], compression="tiff_lzw")
     assert np.array_equal(_load_volume(str(tmp_path / "lzw.tif")), vol)
+
+
+def _slab_writer(path, shape, z0, z1, first):
+    vol = _volume(shape, np.uint16, seed=9)
+    vio.write_planes(path, vio.TiffLayout(shape, np.uint16), vol[z0:z1], z0, write_directory=first)
+
+
+def test_two_processes_write_one_file_concurrently(tmp_path):
+    """what DicedInference.run_file does under torchrun: every rank writes its slab of the shared output file, using
+    the balanced z-slab ranges of the sharding module"""
+    import multiprocessing as mp
+    from neuroclear_b200 import sharding
+    shape = (23, 16, 20)
+    path = str(tmp_path / "ranks.tif")
+    ranges = sharding.balanced_ranges(shape[0], 3)
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_slab_writer, args=(path, shape, z0, z1, r == 0)) for r, (z0, z1) in enumerate(ranges)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert np.array_equal(vio.read_volume(path), _volume(shape, np.uint16, seed=9))
