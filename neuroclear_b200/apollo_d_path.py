@@ -98,6 +98,11 @@ class _nullcontext:
         return False
 
 
+#: when set to a list, allreduce_mean_gradients appends a (start, end) CUDA-event pair around every bucket
+#: all-reduce (bench.py's `train_step_dp.allreduce_ms`)
+ALLREDUCE_EVENTS = None
+
+
 def allreduce_mean_gradients(params, group=None):
     """Data-parallel training: average the gradients of `params` over the ranks of `group` with ONE
     all-reduce of a flat fp32 bucket (11 M discriminator parameters = 44 MB: a single NCCL call over NVLink).
@@ -108,7 +113,14 @@ def allreduce_mean_gradients(params, group=None):
     if world == 1 or not with_grad:
         return
     flat = torch.cat([p.grad.reshape(-1) for p in with_grad])
+    timed = ALLREDUCE_EVENTS is not None and flat.is_cuda
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if timed:
+        e1.record()
+        ALLREDUCE_EVENTS.append((e0, e1))
     flat.div_(world)
     off = 0
     for p in with_grad:

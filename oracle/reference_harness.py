@@ -1,6 +1,10 @@
-"""Imports the UNMODIFIED reference from /root/reference with stub modules for its absent third-party imports.
-Test infrastructure — see oracle/__init__.py.  Only usable in the build container (the GPU box has no
-/root/reference); used by oracle/make_golden.py to pin the restatements and to write tests/golden/.
+"""Imports the UNMODIFIED reference with stub modules for its absent third-party imports.
+Test infrastructure — see oracle/__init__.py.
+
+Two homes for the reference: /root/reference (sources; the build container only — oracle/make_golden.py pins the
+restatements against it and writes tests/golden/) and oracle/_ref/neuroclear (the same modules byte-compiled by
+oracle/build_ref.py; git-ignored, travels to the GPU box).  bench.py / the -m gpu tests pass compiled=True: they
+never read /root/reference.
 
 Stubs: skimage{,.io,.exposure,.transform}, np.float.  skimage.exposure.rescale_intensity is
 routed to oracle.assemble.rescale_intensity (the one unpinned piece).
@@ -15,6 +19,7 @@ from argparse import Namespace
 import numpy as np
 
 REFERENCE_ROOT = "/root/reference"
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "neuroclear")
 _VOLUME = {"array": None}
 
 
@@ -22,8 +27,13 @@ def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
 
 
-def install():
-    """Put the reference on sys.path behind stubs; idempotent."""
+def compiled_available() -> bool:
+    return os.path.exists(os.path.join(COMPILED_ROOT, "models", "networks.pyc"))
+
+
+def install(compiled: bool = False):
+    """Put the reference on sys.path behind stubs; idempotent.  compiled=True: only oracle/_ref (never the sources)."""
+    root = COMPILED_ROOT if compiled or not available() else REFERENCE_ROOT
     if "skimage" not in sys.modules:
         from . import assemble as _asm
         if not hasattr(np, "float"):
@@ -37,8 +47,9 @@ def install():
         ex.match_histograms = lambda a, b: a
         sk.io, sk.exposure, sk.transform = io, ex, tr
         sys.modules.update({"skimage": sk, "skimage.io": io, "skimage.exposure": ex, "skimage.transform": tr})
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return root
 
 
 def set_volume(vol: np.ndarray):

@@ -246,11 +246,14 @@ def test_product_never_imports_the_oracle():
                 [node.module or ""] if isinstance(node, ast.ImportFrom) else []
             assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), fn
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
-    allowed = {"cpu_baseline_sample", "run_reference", "train_step_cpu_baseline"}
-    for fdef in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
-        for node in ast.walk(fdef):
-            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
-                assert fdef.name in allowed, fdef.name
+    allowed = {"CpuSample", "train_step_cpu_baseline"}     # the cpu_baseline / --impl reference legs
+    for top in tree.body:
+        if isinstance(top, (ast.FunctionDef, ast.ClassDef)):
+            for node in ast.walk(top):
+                if isinstance(node, (ast.ImportFrom, ast.Import)):
+                    mods = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+                    if any(m.split(".")[0] == "oracle" for m in mods):
+                        assert top.name in allowed, top.name
     for node in tree.body:                                              # nothing at module level
         assert not (isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle")
 
