@@ -31,6 +31,10 @@ typedef void* nc_stream_t; /* cudaStream_t */
 /* ---- runtime ------------------------------------------------------------------------------------------- */
 int nc_abi_version(void);
 const char* nc_last_error(void);
+/* "NC_SOURCE_HASH=<sha256>": digest of the csrc/ sources, headers, include/neuroclear_b200.h and the nvcc flags this
+ * binary was compiled from (neuroclear_b200/build.py passes it as -DNC_SOURCE_HASH); build() recompiles when the
+ * digest of the tree differs, so a stale shipped .so cannot pass for the source */
+const char* nc_build_source_hash(void);
 /* number of SMs of the current device (148 on B200); <0 on error */
 int nc_device_sm_count(void);
 /* test hook: cap the persistent grid of the tensor-core conv kernels at n CTAs (0 = one per SM) so that small test

@@ -19,6 +19,7 @@ U4 = C.c_uint64 * 4
 SIGNATURES = {
     "nc_abi_version": (C.c_int, []),
     "nc_last_error": (C.c_char_p, []),
+    "nc_build_source_hash": (C.c_char_p, []),
     "nc_device_sm_count": (C.c_int, []),
     "nc_debug_set_max_ctas": (None, [i32]),
     "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),

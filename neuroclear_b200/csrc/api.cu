@@ -12,6 +12,11 @@ extern "C" {
 int nc_abi_version(void) { return NC_ABI_VERSION; }
 const char* nc_last_error(void) { return last_error(); }
 
+#ifndef NC_SOURCE_HASH
+#define NC_SOURCE_HASH "unstamped"
+#endif
+const char* nc_build_source_hash(void) { return "NC_SOURCE_HASH=" NC_SOURCE_HASH; }
+
 void nc_debug_set_max_ctas(int32_t n) { debug_set_max_ctas(n); }
 
 int nc_device_sm_count(void) {

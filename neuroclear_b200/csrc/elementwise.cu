@@ -526,7 +526,9 @@ __global__ void percentile_lerp_kernel(const SelectState* st, double t_lo, doubl
   out64[1] = p_hi;
   out32[0] = static_cast<float>(p_lo);
   out32[1] = static_cast<float>(p_hi);
-  out32[2] = static_cast<float>(p_hi - p_lo);
+  // skimage tests `imin != imax` on the float64 percentiles (exposure.rescale_intensity); the degenerate case is
+  // flagged with a NaN span so that the float32 rounding of a tiny non-zero span cannot take the wrong branch
+  out32[2] = p_lo != p_hi ? static_cast<float>(p_hi - p_lo) : __int_as_float(0x7fc00000);
 }
 
 int select_init(const unsigned long long* ranks, void* st, cudaStream_t stream) {
@@ -571,10 +573,10 @@ rescale_crop_kernel(const float* __restrict__ vol, int vol_z0, int Py, int Px, i
   float v = __ldcs(vol + (static_cast<size_t>(z - vol_z0) * Py + y) * Px + x);
   if (norm3) {
     const float lo = norm3[0], hi = norm3[1], span = norm3[2];
-    if (span != 0.f) {
-      v = fminf(fmaxf(v, lo), hi);              // np.clip(image, imin, imax)
+    v = fminf(fmaxf(v, lo), hi);                // np.clip(image, imin, imax) — in both branches
+    if (span == span) {
       v = __fdiv_rn(__fsub_rn(v, lo), span);    // (image - imin) / (imax - imin)
-    } else {
+    } else {                                    // imin == imax: every voxel is imin, then np.clip(image, omin, omax)
       v = fminf(fmaxf(v, 0.f), 1.f);
     }
   }

@@ -8,6 +8,7 @@ Same class names, constructor (``opt`` namespace), methods and attributes as the
 from __future__ import annotations
 
 import os
+import struct
 from collections import OrderedDict
 from dataclasses import dataclass
 
@@ -140,7 +141,7 @@ def _load_volume(path):
     from . import volume_io
     try:
         return volume_io.read_volume(path)
-    except NeuroclearError:
+    except (NeuroclearError, KeyError, struct.error):       # not a plain strip TIFF: let cv2's codec try
         pass
     import cv2
     ok, pages = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)

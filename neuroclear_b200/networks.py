@@ -78,6 +78,9 @@ def init_weights(net, init_type="normal", init_gain=0.02):
 
     print("initialize network with %s" % init_type)
     net.apply(init_func)
+    for m in net.modules():            # the initialisers write through .data: no version bump — say so explicitly
+        if hasattr(m, "invalidate"):
+            m.invalidate()
 
 
 def init_net(net, init_type="normal", init_gain=0.02, gpu_ids=[]):
@@ -104,6 +107,18 @@ class _ConvStack(nn.Module):
     def __init__(self, n_convs, cin, cout, norm_layer):
         super().__init__()
         self.convolution = nn.Sequential(*_conv_block(n_convs, cin, cout, norm_layer))
+
+
+def _weights_signature(params):
+    """(data_ptr, version) per tensor PLUS an exact checksum of the values: the int64 sum of the fp32 bit patterns of
+    all parameters (one cat + one reduction on the device, 8 bytes to the host).  The version counter alone is not
+    enough: writes through ``p.data`` — the idiom of init_weights, EMA updates, ``p.data.copy_()`` checkpoint loaders —
+    do not bump it, and the engines would silently keep stale packed weights."""
+    ps = [p.detach() for p in params]
+    with torch.no_grad():
+        flat = torch.cat([p.reshape(-1).to(torch.float32) for p in ps])
+        chk = int(flat.view(torch.int32).sum(dtype=torch.int64).item())
+    return tuple((p.data_ptr(), p._version) for p in ps) + (chk,)
 
 
 class _UnetDeconvFn(torch.autograd.Function):
@@ -154,12 +169,17 @@ class Unet_deconv(nn.Module):
         self._engine = None
         self._engine_sig = None
         self._train_engine = None
-        self._train_sig = None
 
-    # the packed fp16 weight cache follows the parameters: any in-place update, load_state_dict or device move
-    # changes (data_ptr, _version) and triggers a repack on the next forward.
+    # the packed fp16 weight cache follows the parameters.  Inference: repack when (data_ptr, _version, checksum of
+    # the values) changed — in-place updates, load_state_dict, device moves and writes through .data are all seen.
+    # Training: the weights change every iteration, so the training engine re-packs on EVERY forward (12 small
+    # launches) and needs no signature at all.
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return _weights_signature(self.parameters())
+
+    def invalidate(self):
+        """Drop the packed-weight caches (call after writing parameters through a side door)."""
+        self._engine_sig = None
 
     def engine(self) -> UnetDeconvEngine:
         p = next(self.parameters())
@@ -180,12 +200,9 @@ class Unet_deconv(nn.Module):
         if not p.is_cuda:
             raise NeuroclearError("Unet_deconv (B200): parameters are on the CPU; there is no CPU fallback — "
                                   "move the network to a CUDA device")
-        sig = self._signature()
         if self._train_engine is None or self._train_engine.device != p.device:
-            self._train_engine, self._train_sig = UnetDeconvTrainEngine(p.device), None
-        if self._train_sig != sig:
-            self._train_engine.load_state_dict(self.state_dict())
-            self._train_sig = sig
+            self._train_engine = UnetDeconvTrainEngine(p.device)
+        self._train_engine.load_state_dict(self.state_dict())
         return self._train_engine
 
     def forward(self, inputs):
@@ -209,7 +226,7 @@ class _DeepLinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, *params):
-        eng = module.engine()
+        eng = module.engine(training=True)
         with torch.cuda.device(x.device):
             y = eng.forward(x.detach().to(torch.float32)[:, 0].contiguous())
         ctx.module, ctx.eng, ctx.saved = module, eng, eng.saved
@@ -240,18 +257,25 @@ class DeepLinearGenerator(nn.Module):
         self._engine = None
         self._engine_sig = None
 
-    def engine(self):
+    def engine(self, training=False):
         from .deeplinear_engine import DeepLinearEngine
         p = next(self.parameters())
         if not p.is_cuda:
             raise NeuroclearError("DeepLinearGenerator (B200): parameters are on the CPU; there is no CPU fallback")
-        sig = tuple((q.data_ptr(), q._version) for q in self.parameters())
         if self._engine is None or self._engine.device != p.device:
             self._engine, self._engine_sig = DeepLinearEngine(p.device), None
+        if training:                         # weights change every iteration — always re-pack, no host check
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_sig = None
+            return self._engine
+        sig = _weights_signature(self.parameters())
         if self._engine_sig != sig:
             self._engine.load_state_dict(self.state_dict())
             self._engine_sig = sig
         return self._engine
+
+    def invalidate(self):
+        self._engine_sig = None
 
     def forward(self, input):
         if input.dim() != 5 or input.shape[1] != 1:

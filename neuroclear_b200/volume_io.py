@@ -50,6 +50,8 @@ class TiffVolume:
             shape = dtype = None
             while ifd:
                 tags, ifd = self._read_ifd(f, ifd)
+                if 256 not in tags or 257 not in tags:
+                    raise NeuroclearError("%s: page without ImageWidth / ImageLength tags" % path)
                 w, h = tags[256][0], tags[257][0]
                 bits = tags.get(258, [1])[0]
                 if tags.get(259, [1])[0] != 1:
@@ -183,7 +185,10 @@ class TiffLayout:
         self.header = 16 if self.big else 8
         self.ifd_size = (8 + ntags * 20 + 8) if self.big else (2 + ntags * 12 + 4)
         self.data_offset = self.header
-        self.ifd_offset = self.header + z * self.plane
+        # TIFF 6.0: an IFD must begin on a word boundary (BigTIFF: 8 bytes); an odd Y*X*Z of uint8 planes would put
+        # it on an odd offset, so pad (the gap bytes are never referenced)
+        align = 8 if self.big else 2
+        self.ifd_offset = -(-(self.header + z * self.plane) // align) * align
         self.file_size = self.ifd_offset + z * self.ifd_size
 
     def plane_offset(self, z):

@@ -394,12 +394,9 @@ def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
     os.makedirs(GOLD, exist_ok=True)
-    # Every function seeds what it draws (torch Generators, np.random.seed, seeded state dicts), so the fixtures do not
-    # depend on the order of the calls.  One historical exception: the committed apollo_d_path_32.npz was recorded
-    # before golden_apollo_discriminator_path seeded torch's global RNG (the generators' init_weights() draw, i.e. its
-    # fake / rec volumes); re-running it writes different — equally valid — fake / rec volumes.  The fixture is
-    # self-contained (the tests read real / fake / rec from it), and tests/test_oracle_golden.py re-derives its
-    # losses and gradients with the oracle on every CPU run.
+    # Every function seeds what it draws (torch Generators, torch.manual_seed, np.random.seed, seeded state dicts), so
+    # the fixtures do not depend on the order of the calls and every one of them regenerates bit-identically
+    # (apollo_d_path_32.npz was re-recorded with the seeded function in round 2).
     golden_geometry()
     golden_dice_assemble()
     golden_unet()

@@ -112,6 +112,25 @@ def test_percentile_select_exact(cuda, n, dist):
         assert tuple(p64.cpu().tolist()) == (float(ref[0]), float(ref[1]))
 
 
+def test_rescale_degenerate_percentile_range_follows_skimage(cuda):
+    """imin == imax (e.g. a flat volume, or sat_level (50, 50)): skimage clips to [imin, imax] FIRST, so every voxel
+    becomes imin, and only then to [0, 1]; the branch is chosen on the float64 percentiles."""
+    from neuroclear_b200.dicing import PercentileSelect, dice_geometry, rescale_u16_crop
+    from oracle import assemble, geometry as ogeo
+    rng = np.random.default_rng(9)
+    size = (9, 9, 9)
+    g, og = dice_geometry(size, 8, 2, 1), ogeo.dice_geometry(size, 8, 2, 1)
+    vis = rng.random(g.padded, dtype=np.float32)
+    for sat in [(50.0, 50.0), (0.25, 99.75)]:
+        ref, _ = assemble.finish(vis, og, True, sat_level=sat)
+        dv = torch.from_numpy(vis).to(cuda)
+        norm3, _ = PercentileSelect(cuda).run(dv.view(-1), dv.numel(), sat)
+        got = rescale_u16_crop(dv, 0, g, norm3, 0, size[0]).cpu().numpy()
+        assert np.array_equal(got, ref), sat
+        if sat[0] == sat[1]:
+            assert len(np.unique(got)) == 1
+
+
 # ------------------------------------------------------------------------------------------------ network layers
 def _ndhwc(t):      # (N,C,D,H,W) -> (N,D,H,W,C) contiguous
     return t.permute(0, 2, 3, 4, 1).contiguous()

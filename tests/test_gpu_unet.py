@@ -93,6 +93,19 @@ def test_weight_updates_invalidate_packed_cache(net, cuda):
         m.one_by_one_2.bias.copy_(saved)
         y2 = net(x)
     assert not torch.equal(y0, y1) and torch.equal(y0, y2)
+    # writes through .data do NOT bump _version (init_weights, EMA, p.data.copy_ loaders): the value checksum sees them
+    with torch.no_grad():
+        v0 = m.one_by_one_2.bias._version
+        m.one_by_one_2.bias.data.add_(1.0)
+        assert m.one_by_one_2.bias._version == v0
+        y3 = net(x)
+        m.one_by_one_2.bias.data.copy_(saved)
+        y4 = net(x)
+        w = m.double_conv2.convolution[3].weight
+        w.data.neg_()                                 # a pure sign flip keeps every norm: the bit-pattern sum moves
+        y5 = net(x)
+        w.data.neg_()
+    assert not torch.equal(y0, y3) and torch.equal(y0, y4) and not torch.equal(y0, y5)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}                      # save_networks round trip
     m.cpu()
     m.cuda(0)

@@ -1,8 +1,6 @@
 """nc_augment_crop_u16 / neuroclear_b200.augment on the GPU against the fixture recorded from the reference's
 transform pipeline (bit-exact).  The kernel's per-voxel arithmetic is already checked on the CPU
-(tests/test_augment_host.py builds csrc/augment_math.h with gcc); this file was written after the GPU budget of
-round 1 was spent, so its first hardware run is the driver's — hence the non-strict xfail marker (an XPASS is the
-expected outcome; remove the marker in round 2)."""
+(tests/test_augment_host.py builds csrc/augment_math.h with gcc).  First hardware run: the driver's round-1 GPU suite (passed); strict since round 2."""
 import os
 import random
 
@@ -10,9 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (round 1 GPU "
-                                                                      "budget spent); CPU build of the same "
-                                                                      "arithmetic is bit-exact")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 

@@ -1,11 +1,10 @@
 """DicedInference.run_file: TIFF in -> diced inference -> TIFF out, equal to the in-memory path.  Composition of
-parts that are each verified (volume_io on the CPU against Pillow, run_slab on the GPU); written after the GPU budget
-of round 1 was spent, hence the non-strict xfail marker (an XPASS is the expected outcome; remove it in round 2)."""
+parts that are each verified (volume_io on the CPU against Pillow, run_slab on the GPU).  First hardware run: the driver's round-1
+GPU suite (passed); strict since round 2."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (round 1 GPU "
-                                                                      "budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_file_to_file_equals_in_memory(tmp_path):

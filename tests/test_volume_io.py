@@ -136,3 +136,18 @@ def test_two_processes_write_one_file_concurrently(tmp_path):
         p.join(60)
         assert p.exitcode == 0
     assert np.array_equal(vio.read_volume(path), _volume(shape, np.uint16, seed=9))
+
+
+def test_ifd_chain_is_word_aligned_for_odd_uint8_volumes(tmp_path):
+    """TIFF 6.0 requires IFDs on a word boundary; an odd Y*X*Z of uint8 planes used to put the chain on an odd offset."""
+    from PIL import Image
+    vol = np.random.default_rng(3).integers(0, 256, (3, 5, 7), dtype=np.uint8)       # 105 data bytes
+    for big in (False, True):
+        path = str(tmp_path / ("odd_%d.tif" % big))
+        layout = vio.write_volume(path, vol, bigtiff=big)
+        assert layout.ifd_offset % (8 if big else 2) == 0 and layout.file_size == os.path.getsize(path)
+        assert np.array_equal(vio.read_volume(path), vol)
+    im = Image.open(str(tmp_path / "odd_0.tif"))
+    for z in range(3):
+        im.seek(z)
+        assert np.array_equal(np.array(im), vol[z])
