@@ -42,6 +42,7 @@ class DicedInference:
             self.engine.load_state_dict(state_dict)
             self.select = PercentileSelect(self.device)
         self._plan_key = None
+        self._copy_stream = None
         self.last = {}
         self.out_dtype = torch.uint16     # follows the input volume's dtype (--data_type uint16 | uint8)
 
@@ -75,7 +76,29 @@ class DicedInference:
         z0, z1 = plan["in_planes"]
         return volume_host[z0:z1].to(self.device, non_blocking=True), z0
 
-    def infer_cubes(self, vol_dev, vol_z0, plan, queue=None):
+    def upload_chunked(self, slab_host: torch.Tensor, plan, chunks=16):
+        """H2D of this rank's input planes on a side stream, in z-chunks, so that the first cube batches start while
+        the rest of the slab is still crossing PCIe.  Returns (device slab, [(z_end, event)...]): infer_cubes makes
+        the compute stream wait for exactly the chunks a batch reads."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        z0, z1 = plan["in_planes"]
+        n = z1 - z0
+        vol_dev = torch.empty(slab_host.shape, dtype=slab_host.dtype, device=self.device)
+        ready = []
+        step = max(1, -(-n // chunks))
+        self._copy_stream.wait_stream(torch.cuda.current_stream())      # the allocation above is stream-ordered
+        with torch.cuda.stream(self._copy_stream):
+            for a in range(0, n, step):
+                b = min(n, a + step)
+                vol_dev[a:b].copy_(slab_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                ready.append((z0 + b, ev))
+        vol_dev.record_stream(self._copy_stream)      # allocated on the compute stream, written on the copy stream
+        return vol_dev, ready
+
+    def infer_cubes(self, vol_dev, vol_z0, plan, queue=None, ready=None):
         self.out_dtype = vol_dev.dtype
         geo = plan["geo"]
         c0, c1 = plan["cubes"]
@@ -84,8 +107,14 @@ class DicedInference:
             queue = torch.empty((c1 - c0, r, r, r), dtype=torch.float32, device=self.device)
         nbmax = min(self.batch, max(c1 - c0, 1))
         xbuf = torch.empty((nbmax, e, e, e), dtype=torch.float32, device=self.device)
+        waited = 0
         for b0 in range(c0, c1, nbmax):
             nb = min(nbmax, c1 - b0)
+            if ready:       # wait for the uploaded chunks this batch's cubes read (border and reflection included)
+                need = sharding.input_plane_range(geo, b0, b0 + nb)[1]
+                while waited < len(ready) and (waited == 0 or ready[waited - 1][0] < need):
+                    torch.cuda.current_stream().wait_event(ready[waited][1])
+                    waited += 1
             x = dice_extract(vol_dev, vol_z0, geo, b0, nb, out=xbuf[:nb])
             self.engine.forward(x, crop=self.border, out=queue[b0 - c0:b0 - c0 + nb], nb_cap=nbmax)
         return queue
@@ -107,11 +136,11 @@ class DicedInference:
         return rescale_u16_crop(vis, s0, geo, norm3, o0, o1 - o0, dtype=self.out_dtype)
 
     # ---------------------------------------------------------------- public API
-    def run_device(self, vol_dev, vol_z0, size):
-        """Inputs already in HBM -> this rank's uint16 output planes in HBM."""
+    def run_device(self, vol_dev, vol_z0, size, ready=None):
+        """Inputs already in HBM (or arriving: `ready` from upload_chunked) -> this rank's uint16 output planes in HBM."""
         with torch.cuda.device(self.device):
             plan = self.plan(size)
-            queue = self.infer_cubes(vol_dev, vol_z0, plan)
+            queue = self.infer_cubes(vol_dev, vol_z0, plan, ready=ready)
             return self.assemble(queue, plan)
 
     def run_slab(self, slab_host: torch.Tensor, slab_z0: int, size, out_host: torch.Tensor = None):
@@ -122,8 +151,8 @@ class DicedInference:
             z0, z1 = plan["in_planes"]
             if slab_z0 != z0 or slab_host.shape[0] != z1 - z0:
                 raise NeuroclearError("run_slab: expected input planes [%d, %d)" % (z0, z1))
-            vol_dev = slab_host.to(self.device, non_blocking=True)
-            out_dev = self.run_device(vol_dev, z0, tuple(size))
+            vol_dev, ready = self.upload_chunked(slab_host, plan)
+            out_dev = self.run_device(vol_dev, z0, tuple(size), ready=ready)
             if out_host is None:
                 out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
             out_host.copy_(out_dev, non_blocking=True)
@@ -163,8 +192,12 @@ class DicedInference:
             raise NeuroclearError("DicedInference.run expects a (Z,Y,X) uint16 or uint8 volume")
         with torch.cuda.device(self.device):
             plan = self.plan(tuple(volume.shape))
-            vol_dev, z0 = self.upload(volume, plan)
-            out_dev = self.run_device(vol_dev, z0, tuple(volume.shape))
+            z0, z1 = plan["in_planes"]
+            if volume.is_pinned():
+                vol_dev, ready = self.upload_chunked(volume[z0:z1], plan)
+            else:
+                (vol_dev, _), ready = self.upload(volume, plan), None
+            out_dev = self.run_device(vol_dev, z0, tuple(volume.shape), ready=ready)
             if out_host is None:
                 out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
             out_host.copy_(out_dev, non_blocking=True)

@@ -108,3 +108,59 @@ def test_two_steps_run_and_losses_stay_finite():
     assert all(np.isfinite(v) for v in m.get_current_losses().values())
     m.test()
     assert tuple(m.rec.shape) == (1, 1, 28, 28, 28) and not m.rec.requires_grad
+
+
+def test_full_iteration_at_108_against_oracle():
+    """BASELINE.json configs[2] at its real size: one optimize_parameters() on a 108^3 crop against the oracle's
+    restatement of the reference iteration (oracle/apollo_step.py — bit-identical to the reference fixture at 32^3,
+    tests/test_oracle_golden.py) run on the host cores with the same weights, crop and np.random draws.
+    Bars: the 11 losses within 2 % (|d| <= 2e-2 max(1, |ref|)); every generator gradient tensor's cosine against the
+    fp32 oracle is printed (and written to gpurun_out/apollo_108_parity.txt) and must be >= 0.9 for the weights that
+    are not pure rounding noise; the updated parameters of all six networks within 2.1 lr."""
+    from oracle import apollo_step
+    S = 108
+    m, before = _model()
+    real = torch.rand((1, 1, S, S, S), generator=torch.Generator().manual_seed(108))
+    np.random.seed(11)
+    m.set_input({"A": real, "A_paths": "crop108"})
+    m.optimize_parameters()
+    torch.cuda.synchronize()
+    got = m.get_current_losses()
+    torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    ref_model = apollo_step.ApolloStep(before, lr=LR)
+    np.random.seed(11)
+    ref_model.set_input(real)
+    assert ref_model.depth == m.projection_depth
+    ref = ref_model.optimize_parameters()
+    lines = ["apollo iteration at %d^3: GPU path vs fp32 oracle" % S]
+    for k in ref:
+        lines.append("  loss_%-12s %.6f   oracle %.6f" % (k, got[k], ref[k]))
+        assert abs(got[k] - ref[k]) <= 2e-2 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+    fake_err = float((m.fake.detach().cpu() - ref_model.fake.detach()).abs().max())
+    lines.append("  fake max-abs %.4g" % fake_err)
+    assert fake_err <= 2e-2
+    worst = 1.0
+    for name in ("G_A", "G_B"):
+        net = getattr(m, "net" + name).module
+        for k, p in net.named_parameters():
+            ref_p = ref_model.p[name][k]
+            assert float((p.detach().cpu() - ref_p.detach()).abs().max()) <= 2.1 * LR, (name, k)
+            if k.endswith(".bias") and k.startswith(NOISE_ONLY):
+                continue
+            a, b = p.grad.detach().double().cpu().reshape(-1), ref_p.grad.double().reshape(-1)
+            cos = float(a @ b / (a.norm() * b.norm() + 1e-300))
+            rel = float((a - b).norm() / (b.norm() + 1e-300))
+            lines.append("  %s %-40s cos %.4f  rel L2 %.3f" % (name, k, cos, rel))
+            worst = min(worst, cos)
+    for name in D_NAMES:
+        for k, p in getattr(m, "net" + name).module.named_parameters():
+            assert float((p.detach().cpu() - ref_model.p[name][k].detach()).abs().max()) <= 2.1 * LR, (name, k)
+    lines.append("  worst generator-gradient cosine %.4f" % worst)
+    print("\n" + "\n".join(lines))
+    try:
+        os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)
+        with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "apollo_108_parity.txt"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+    except OSError:
+        pass
+    assert worst >= 0.9, worst
