@@ -351,6 +351,7 @@ def train_step_dp(dev, rank, world, barrier, crop=148, iters=5, warmup=3):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    torch.cuda.reset_peak_memory_stats(dev)
     try:    # phase 1 has no collective inside: a failure on one rank is agreed on before anyone enters phase 2
         ms_alone, launches, _, model = time_apollo_iterations(dev, crop, iters, warmup, False, rank)
         err = None

@@ -320,6 +320,32 @@ int nc_patchgan_bwd(const float* x, const float* dpred, int32_t n, int32_t h, in
                     const float* const* weights, float* ws, float* dx, float* const* dweights, float* const* dbiases,
                     nc_stream_t stream);
 
+/* ---- remaining Assemble_Dice / test_dice.py options -------------------------------------------
+ * --histogram_match (util/assemble_dice.py:150-151): skimage.exposure.match_histograms(fake, real) of one border-cut
+ * cube (n = roi^3 float32 voxels each), skimage/exposure/histogram_matching.py::_match_cumulative_cdf restated:
+ * np.unique both, quantiles = cumsum(counts) / n, np.interp(src_q, tmpl_q, tmpl_values)[inverse] -> float64 (n).
+ * scratch: nc_hist_match_scratch_bytes(n) bytes of device memory (two sorted copies + radix-sort workspace). */
+int64_t nc_hist_match_scratch_bytes(int64_t n);
+int nc_hist_match_f32(const float* fake, const float* real, int64_t n, void* scratch, int64_t scratch_bytes,
+                      double* out, nc_stream_t stream);
+/* nc_blend_gather_f32 for a queue of float64 cubes (what match_histograms returns): numpy evaluates
+ * `visual_ret[...] += cube / 8` (assemble_dice.py:172) with the float64 loop and stores float32. */
+int nc_blend_gather_f64(const double* pieces, const int64_t* piece_off, const int32_t* piece_z0,
+                        const int32_t padded_zyx[3], const int32_t steps_zyx[3], int32_t roi, int32_t overlap,
+                        int32_t out_z0, int32_t out_nz, float* out, nc_stream_t stream);
+/* --save_projections (test_dice.py:159-177): np.amax(volume[a0:a1 along axis], axis) of a (z,y,x) uint16
+ * (elem_bytes 2) or uint8 (1) volume; a0/a1 are clamped like a numpy slice. out: the 2-D image, same type. */
+int nc_amax_axis(const void* vol, int32_t elem_bytes, int32_t z, int32_t y, int32_t x, int32_t axis, int32_t a0,
+                 int32_t a1, void* out, nc_stream_t stream);
+/* PSNR report (test_dice.py:229-270, util/util.py:56-71,107-115): exact integer moments {sum, sum of squares, min,
+ * max} of a uint8 / uint16 volume; util.normalize(util.standardize(v), np.uint8) per voxel in float64 with
+ * params4 = {mean, std, standardized minimum, 255 / (standardized max - min)}; sum of squared differences of two
+ * uint8 volumes (an exact integer). */
+int nc_volume_moments(const void* vol, int32_t elem_bytes, int64_t n, uint64_t* out4, nc_stream_t stream);
+int nc_standardize_normalize_u8(const void* vol, int32_t elem_bytes, int64_t n, const double* params4, uint8_t* out,
+                                nc_stream_t stream);
+int nc_sqdiff_u8(const uint8_t* a, const uint8_t* b, int64_t n, uint64_t* out1, nc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,8 +234,9 @@ class Assemble_Dice:
         if self.imtype not in ("uint16", "uint8"):
             raise NeuroclearError("Assemble_Dice (B200): --data_type must be uint16 or uint8")
         self.skip_real = opt.skip_real
-        if getattr(opt, "histogram_match", False):
-            raise NotImplementedError("--histogram_match is outside the B200 hot path (SURVEY.md §8f-3)")
+        self.histogram_match = bool(getattr(opt, "histogram_match", False))       # assemble_dice.py:35,150-151
+        if self.histogram_match:
+            print("We will match the histograms of output sub-volumes with input sub-volumes.")
         self.normalize_intensity = opt.normalize_intensity
         if self.normalize_intensity:
             self.p1, self.p99 = opt.sat_level
@@ -253,9 +254,11 @@ class Assemble_Dice:
         for name in self.visual_names:
             if self.skip_real and name == "real":
                 continue
-            self.cube_queue[name] = torch.empty((self.len_cube_queue, r, r, r), dtype=torch.float32,
-                                                device=self.device)
+            # match_histograms returns float64 and the reference queues it as such: the blend then adds in float64
+            dt = torch.float64 if (self.histogram_match and name == "fake") else torch.float32
+            self.cube_queue[name] = torch.empty((self.len_cube_queue, r, r, r), dtype=dt, device=self.device)
             self._count[name] = 0
+        self._hm_scratch = None
 
     def indexTo3DIndex(self, index):
         x = index % self.x_steps
@@ -294,19 +297,42 @@ class Assemble_Dice:
     def addToStack(self, cube):
         """cube: dict with 'real' and 'fake' (1,1,E,E,E) tensors, as BaseModel.get_current_visuals() returns."""
         bc = self.border_cut
+        cut = {}
         for name in self.visual_names:
             t = cube[name]                       # both keys are required, like the reference (:132-133)
-            if self.skip_real and name == "real":
-                continue
             if not t.is_cuda:
                 raise NeuroclearError("Assemble_Dice (B200) takes device tensors; there is no CPU assembly path")
             c = t.reshape(t.shape[-3:])[bc:-bc, bc:-bc, bc:-bc]
             assert tuple(c.shape) == (self.roi_size,) * 3, "the cube dimensions are invalid."
+            cut[name] = c
+        for name in self.visual_names:
+            if self.skip_real and name == "real":
+                continue
             i = self._count[name]
             if i >= self.len_cube_queue:
                 raise NeuroclearError("more cubes added than the volume has")
-            self.cube_queue[name][i].copy_(c)
+            if self.histogram_match and name == "fake":      # :150-151, matched against the input cube
+                self.match_histograms(cut["fake"], cut["real"], out=self.cube_queue[name][i])
+            else:
+                self.cube_queue[name][i].copy_(cut[name])
             self._count[name] = i + 1
+
+    def match_histograms(self, fake, real, out=None):
+        """skimage.exposure.match_histograms(fake, real) of one cube on the device -> float64, same shape."""
+        with torch.cuda.device(self.device):
+            f = fake.to(torch.float32).contiguous()
+            r = real.to(torch.float32).contiguous()
+            n = f.numel()
+            if r.numel() != n:
+                raise NeuroclearError("match_histograms: image and reference must have the same size")
+            need = _lib.load().nc_hist_match_scratch_bytes(n)
+            if self._hm_scratch is None or self._hm_scratch.numel() < need:
+                self._hm_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+            if out is None:
+                out = torch.empty(f.shape, dtype=torch.float64, device=self.device)
+            call("nc_hist_match_f32", ptr(f), ptr(r), i64(n), ptr(self._hm_scratch), i64(self._hm_scratch.numel()),
+                 ptr(out), stream_ptr())
+        return out
 
     def queue_view(self, name="fake"):
         """Device queue (n_cubes, roi, roi, roi): the fast path lets the network head write into it directly."""
@@ -326,7 +352,13 @@ class Assemble_Dice:
                 if self._count[name] != self.len_cube_queue:
                     raise NeuroclearError("assemble_all: %d of %d cubes queued for '%s'" %
                                           (self._count[name], self.len_cube_queue, name))
-                vis = blend_gather(queue.view(-1), off, z0, g, 0, g.padded[0])
+                if queue.dtype == torch.float64:
+                    vis = torch.empty(g.padded, dtype=torch.float32, device=self.device)
+                    _, padded, steps = g.c_arrays()
+                    call("nc_blend_gather_f64", ptr(queue), ptr(off), ptr(z0), padded, steps, g.roi, g.overlap, 0,
+                         g.padded[0], ptr(vis), stream_ptr())
+                else:
+                    vis = blend_gather(queue.view(-1), off, z0, g, 0, g.padded[0])
                 norm3 = None
                 if self.normalize_intensity:
                     norm3, p64 = sel.run(vis, vis.numel(), (self.p1, self.p99))

@@ -390,6 +390,28 @@ def golden_augment():
     np.savez_compressed(os.path.join(GOLD, "augment_20x48x56.npz"), **out)
 
 
+def golden_report():
+    """The PSNR report of test_dice.py:239-253 computed with the REFERENCE's util.util functions (normalize,
+    standardize, get_psnr) on three small uint16 volumes, and the oracle's restatement checked against it."""
+    rh.install()
+    from util import util as refutil
+    from . import postprocess
+    rng = np.random.default_rng(17)
+    shape = (20, 24, 28)
+    gt = (rng.random(shape) ** 3 * 65535).astype(np.uint16)
+    real = np.clip(gt.astype(np.float64) * 0.6 + rng.normal(0, 2500, shape) + 3000, 0, 65535).astype(np.uint16)
+    fake = np.clip(gt.astype(np.float64) * 0.9 + rng.normal(0, 900, shape) + 500, 0, 65535).astype(np.uint16)
+    vols = [real, fake, gt]
+    for _ in range(2):                                                         # test_dice.py:243-249, as written
+        vols = [refutil.normalize(refutil.standardize(v), data_type=np.uint8) for v in vols]
+    p_in = refutil.get_psnr(vols[0], vols[2], 2 ** 8 - 1)
+    p_out = refutil.get_psnr(vols[1], vols[2], 2 ** 8 - 1)
+    mine = postprocess.psnr_report(real, fake, gt)
+    assert mine[0] == p_in and mine[1] == p_out and all(np.array_equal(a, b) for a, b in zip(mine[2:], vols))
+    np.savez_compressed(os.path.join(GOLD, "report_psnr.npz"), real=real, fake=fake, gt=gt, real8=vols[0],
+                        fake8=vols[1], gt8=vols[2], psnr_input_gt=np.array(p_in), psnr_output_gt=np.array(p_out))
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted at /root/reference: golden vectors can only be regenerated in the build container")
@@ -407,6 +429,7 @@ def main():
     golden_deeplinear()
     golden_apollo_step()
     golden_augment()
+    golden_report()
     print("golden vectors written to", GOLD)
 
 

@@ -2,7 +2,7 @@
 Test infrastructure — see oracle/__init__.py.
 
 Two homes for the reference: /root/reference (sources; the build container only — oracle/make_golden.py pins the
-restatements against it and writes tests/golden/) and oracle/_ref/neuroclear (the same modules byte-compiled by
+restatements against it and writes tests/golden/) and oracle/_ref/neuroclear.zip (the same modules byte-compiled by
 oracle/build_ref.py; git-ignored, travels to the GPU box).  bench.py / the -m gpu tests pass compiled=True: they
 never read /root/reference.
 
@@ -19,7 +19,7 @@ from argparse import Namespace
 import numpy as np
 
 REFERENCE_ROOT = "/root/reference"
-COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "neuroclear")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "neuroclear.zip")
 _VOLUME = {"array": None}
 
 
@@ -28,7 +28,7 @@ def available() -> bool:
 
 
 def compiled_available() -> bool:
-    return os.path.exists(os.path.join(COMPILED_ROOT, "models", "networks.pyc"))
+    return os.path.exists(COMPILED_ROOT)
 
 
 def install(compiled: bool = False):

@@ -202,3 +202,29 @@ def test_apollo_discriminator_path_oracle_matches_reference_fixture():
     for n in apollo_step.D_NAMES:
         for k, t in m.p[n].items():
             assert np.abs(t.detach().numpy().reshape(-1)[::61] - z["after_%s.%s" % (n, k)]).max() <= 1e-7, (n, k)
+
+
+def test_psnr_report_matches_reference_fixture():
+    """oracle.postprocess (normalize / standardize / get_psnr, test_dice.py:239-253) against the values recorded from
+    the reference's own util.util functions."""
+    from oracle import postprocess
+    z = np.load(os.path.join(GOLDEN, "report_psnr.npz"))
+    p_in, p_out, r8, f8, g8 = postprocess.psnr_report(z["real"], z["fake"], z["gt"])
+    assert p_in == float(z["psnr_input_gt"]) and p_out == float(z["psnr_output_gt"])
+    assert np.array_equal(r8, z["real8"]) and np.array_equal(f8, z["fake8"]) and np.array_equal(g8, z["gt8"])
+
+
+def test_match_histograms_restatement_properties():
+    """skimage is absent (parity unpinned, oracle/postprocess.py): check the defining properties of CDF matching —
+    the output takes values inside the template's range, is a monotone function of the input, and matching an array
+    to itself (or to a permutation of itself) is the identity."""
+    from oracle import postprocess
+    rng = np.random.default_rng(4)
+    a = rng.random((6, 7, 8)).astype(np.float32)
+    b = (rng.integers(0, 4000, (6, 7, 8)) / 65535.0).astype(np.float32)
+    m = postprocess.match_histograms(a, b)
+    assert m.dtype == np.float64 and m.shape == a.shape and m.min() >= b.min() and m.max() <= b.max()
+    order = np.argsort(a.ravel(), kind="stable")
+    assert np.all(np.diff(m.ravel()[order]) >= 0)
+    assert np.array_equal(postprocess.match_histograms(b, b), b.astype(np.float64))
+    assert np.array_equal(postprocess.match_histograms(b, rng.permutation(b.ravel()).reshape(b.shape)), b.astype(np.float64))
