@@ -130,9 +130,12 @@ def allreduce_mean_gradients(params, group=None):
 
 
 class ApolloDiscriminatorPath:
-    def __init__(self, opt, device, group=None, distributed=None):
+    """with_B=False: the ablation of models/axial_to_lateral_gan_dryops_model.py — no G_B, no D_B_*, no cycle term."""
+
+    def __init__(self, opt, device, group=None, distributed=None, with_B=True):
         import torch.distributed as dist
         self.opt = opt
+        self.with_B = with_B
         self.device = torch.device(device)
         self.group = group
         self.distributed = dist.is_initialized() if distributed is None else distributed
@@ -141,14 +144,14 @@ class ApolloDiscriminatorPath:
                                                opt.init_gain, False, gpu_ids, dimension=2)
         self.netD_A_axial = mk(opt.output_nc)      # creation order of apollo_model.py:99-123
         self.netD_A_lateral = mk(opt.output_nc)
-        self.netD_B_axial = mk(opt.input_nc)
-        self.netD_B_lateral = mk(opt.input_nc)
+        if with_B:
+            self.netD_B_axial = mk(opt.input_nc)
+            self.netD_B_lateral = mk(opt.input_nc)
         self.criterionGAN = discriminator.GANLoss(opt.gan_mode).to(self.device)
         self.criterionCycle = discriminator.L1Loss()
-        self.optimizer_D = FusedAdam(
-            itertools.chain(self.netD_A_axial.parameters(), self.netD_A_lateral.parameters(),
-                            self.netD_B_axial.parameters(), self.netD_B_lateral.parameters()),
-            lr=opt.lr, betas=(opt.beta1, 0.999))
+        nets = [self.netD_A_axial, self.netD_A_lateral] + ([self.netD_B_axial, self.netD_B_lateral] if with_B else [])
+        self.optimizer_D = FusedAdam(itertools.chain(*[n.parameters() for n in nets]),
+                                     lr=opt.lr, betas=(opt.beta1, 0.999))
         s = float(sum(opt.lambda_plane))
         self.lambda_plane_target, self.lambda_slice, self.lambda_proj = [f / s for f in opt.lambda_plane]
         self.lateral_axis, self.axial_1_axis, self.axial_2_axis = 0, 1, 2
@@ -156,7 +159,8 @@ class ApolloDiscriminatorPath:
         self.projection_depth = opt.projection_depth
 
     def discriminators(self):
-        return [self.netD_A_lateral, self.netD_A_axial, self.netD_B_lateral, self.netD_B_axial]
+        return [self.netD_A_lateral, self.netD_A_axial] + \
+            ([self.netD_B_lateral, self.netD_B_axial] if self.with_B else [])
 
     # ---- set_input (:142-160): the projection depth is drawn once per step
     def draw_projection_depth(self):
@@ -212,8 +216,9 @@ class ApolloDiscriminatorPath:
         self.optimizer_D.zero_grad()
         self.backward_D_A_lateral(real, fake)
         self.backward_D_A_axial(real, fake)
-        self.backward_D_B_lateral(real, rec)
-        self.backward_D_B_axial(real, rec)
+        if self.with_B:
+            self.backward_D_B_lateral(real, rec)
+            self.backward_D_B_axial(real, rec)
         if self.distributed:    # one crop per GPU; gradients averaged over the ranks before the update
             allreduce_mean_gradients(self.optimizer_D.params, self.group)
         self.optimizer_D.step()
@@ -228,6 +233,9 @@ class ApolloDiscriminatorPath:
         self.loss_G_A_axial = g(self.proj_f(fake, self.netD_A_axial, 1), True) * self.lambda_slice + \
             g(self.proj_f(fake, self.netD_A_axial, 2), True) * self.lambda_slice
         self.loss_G_A = self.loss_G_A_lateral + self.loss_G_A_axial * 0.5
+        if not self.with_B:                                   # dryops_model.py:209-222
+            self.loss_G = self.loss_G_A
+            return self.loss_G
         self.loss_G_B_lateral = g(self.iter_f(rec, self.netD_B_lateral, 0), True) * self.lambda_plane_target
         self.loss_G_B_axial = g(self.iter_f(rec, self.netD_B_axial, 1), True) * self.lambda_slice + \
             g(self.iter_f(rec, self.netD_B_axial, 2), True) * self.lambda_slice

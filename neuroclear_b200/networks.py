@@ -221,6 +221,62 @@ class Unet_deconv(nn.Module):
             return eng.forward(x)[:, None]
 
 
+class Unet_vanilla(nn.Module):
+    """reference networks.py:540-608 (define_G 'unet_vanilla'): the 4-level U-Net on the same sm_100a kernels
+    (neuroclear_b200.unet_vanilla_engine).  Same children / state_dict as the reference.  Inference path (no_grad /
+    parameters frozen); training this generator is not on the B200 path."""
+
+    def __init__(self, input_nc, output_nc, norm_layer=None, dimension=3):
+        super().__init__()
+        if dimension != 3 or input_nc != 1 or output_nc != 1:
+            raise NotImplementedError("the B200 path implements the 3-D, 1-channel unet_vanilla of the reference")
+        norm_layer = norm_layer or get_norm_layer("instance", 3)
+        probe = norm_layer(1)
+        if not isinstance(probe, nn.InstanceNorm3d) or probe.affine or probe.track_running_stats:
+            raise NotImplementedError("unet_vanilla on B200 is built for --norm instance (affine=False)")
+        nc = input_nc * 64
+        self.double_conv1 = _ConvStack(2, input_nc, nc, norm_layer)
+        self.double_conv2 = _ConvStack(2, nc, nc * 2, norm_layer)
+        self.double_conv3 = _ConvStack(2, nc * 2, nc * 4, norm_layer)
+        self.bottom_layer = _ConvStack(2, nc * 4, nc * 8, norm_layer)
+        self.t_conv3 = nn.ConvTranspose3d(nc * 8, nc * 4, 2, 2)
+        self.ex_double_conv3 = _ConvStack(2, nc * 8, nc * 4, norm_layer)
+        self.t_conv2 = nn.ConvTranspose3d(nc * 4, nc * 2, 2, 2)
+        self.ex_double_conv2 = _ConvStack(2, nc * 4, nc * 2, norm_layer)
+        self.t_conv1 = nn.ConvTranspose3d(nc * 2, nc, 2, 2)
+        self.ex_conv1_1 = _ConvStack(2, nc * 2, nc, norm_layer)
+        self.one_by_one = nn.Conv3d(nc, output_nc, 1, 1, 0)
+        self._engine = None
+        self._engine_sig = None
+
+    def invalidate(self):
+        self._engine_sig = None
+
+    def engine(self):
+        from .unet_vanilla_engine import UnetVanillaEngine
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise NeuroclearError("Unet_vanilla (B200): parameters are on the CPU; there is no CPU fallback")
+        if self._engine is None or self._engine.device != p.device:
+            self._engine, self._engine_sig = UnetVanillaEngine(p.device), None
+        sig = _weights_signature(self.parameters())
+        if self._engine_sig != sig:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_sig = sig
+        return self._engine
+
+    def forward(self, inputs):
+        if inputs.dim() != 5 or inputs.shape[1] != 1:
+            raise NeuroclearError("Unet_vanilla expects (N, 1, D, H, W)")
+        if not inputs.is_cuda:
+            raise NeuroclearError("Unet_vanilla (B200): input is on the CPU; there is no CPU fallback")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("training unet_vanilla is not on the B200 path (use it under torch.no_grad(); "
+                                      "the README trains unet_deconv)")
+        with torch.cuda.device(inputs.device):
+            return self.engine().forward(inputs.detach().to(torch.float32)[:, 0].contiguous())[:, None]
+
+
 class _DeepLinearFn(torch.autograd.Function):
     """DeepLinearGenerator under autograd on neuroclear_b200.deeplinear_engine (input gradient included)."""
 
@@ -294,9 +350,11 @@ def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, in
     norm_layer = get_norm_layer(norm_type=norm, dimension=dimension)
     if netG == "unet_deconv":
         net = Unet_deconv(1, output_nc, norm_layer=norm_layer, dimension=dimension)  # input_nc hard-coded 1 (:174)
+    elif netG == "unet_vanilla":
+        net = Unet_vanilla(1, output_nc, norm_layer=norm_layer, dimension=dimension)  # networks.py:175-176
     elif netG == "deep_linear_gen":
         net = DeepLinearGenerator(input_nc, output_nc)                               # networks.py:193-194
     else:
-        raise NotImplementedError("Generator model name [%s] is not on the B200 hot path (unet_deconv and "
+        raise NotImplementedError("Generator model name [%s] is not on the B200 path (unet_deconv, unet_vanilla and "
                                   "deep_linear_gen are)" % netG)
     return init_net(net, init_type, init_gain, gpu_ids)

@@ -390,6 +390,29 @@ def golden_augment():
     np.savez_compressed(os.path.join(GOLD, "augment_20x48x56.npz"), **out)
 
 
+def golden_unet_vanilla():
+    """Reference define_G('unet_vanilla') (networks.py:540-608) on two small inputs; the oracle restatement must agree
+    exactly (same torch CPU kernels)."""
+    rh.install()
+    from models import networks
+    from . import unet_vanilla as uv
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_G(1, 1, 64, "unet_vanilla", "instance", False, "kaiming", 0.02, [], dimension=3)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == uv.state_dict_shapes()
+    sd = uv.random_state_dict(seed=3, bias_std=0.1)
+    net.load_state_dict(sd)
+    net.eval()
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for name, shape in (("a", (1, 1, 16, 24, 32)), ("b", (2, 1, 24, 16, 16))):
+        x = torch.rand(shape, generator=g) ** 3
+        with torch.no_grad():
+            y = net(x)
+        assert torch.equal(y, uv.unet_vanilla_forward(x, sd))
+        out["x_" + name], out["y_" + name] = x.numpy(), y.numpy()
+    np.savez_compressed(os.path.join(GOLD, "unet_vanilla_small.npz"), **out)
+
+
 def golden_report():
     """The PSNR report of test_dice.py:239-253 computed with the REFERENCE's util.util functions (normalize,
     standardize, get_psnr) on three small uint16 volumes, and the oracle's restatement checked against it."""
@@ -430,6 +453,7 @@ def main():
     golden_apollo_step()
     golden_augment()
     golden_report()
+    golden_unet_vanilla()
     print("golden vectors written to", GOLD)
 
 

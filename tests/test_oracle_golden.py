@@ -228,3 +228,13 @@ def test_match_histograms_restatement_properties():
     assert np.all(np.diff(m.ravel()[order]) >= 0)
     assert np.array_equal(postprocess.match_histograms(b, b), b.astype(np.float64))
     assert np.array_equal(postprocess.match_histograms(b, rng.permutation(b.ravel()).reshape(b.shape)), b.astype(np.float64))
+
+
+def test_unet_vanilla_oracle_matches_reference_fixture():
+    from oracle import unet_vanilla as uv
+    f = np.load(os.path.join(GOLDEN, "unet_vanilla_small.npz"))
+    sd = uv.random_state_dict(seed=3, bias_std=0.1)
+    assert sum(v.numel() for v in sd.values()) == sum(int(np.prod(s)) for s in uv.state_dict_shapes().values())
+    for name in "ab":
+        y = uv.unet_vanilla_forward(torch.from_numpy(f["x_" + name]), sd)
+        assert np.abs(y.numpy() - f["y_" + name]).max() <= 1e-6
