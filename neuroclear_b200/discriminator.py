@@ -219,14 +219,59 @@ class NLayerDiscriminator(nn.Module):
         return x
 
 
+class NLayerDiscriminatorSN(nn.Module):
+    """reference networks.py:1069-1110 (netD 'basic_SN' / 'n_layers_SN'): the PatchGAN without
+    normalisation layers, every convolution wrapped in torch.nn.utils.spectral_norm.  The children ARE the
+    reference's (spectral_norm(nn.Conv2d) — same state_dict: model.N.{bias, weight_orig, weight_u, weight_v});
+    torch's hook performs the power iteration and produces weight_orig / sigma (a handful of mat-vecs on a
+    (Cout, 16 Cin) matrix: parameter plumbing), and every convolution + LeakyReLU, forward and backward, runs on
+    nc_conv2d_k4_* with that weight."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_sigmoid=False, dimension=2):
+        super().__init__()
+        if dimension != 2:
+            raise NotImplementedError("the B200 discriminator path implements 2-D PatchGANs")
+        if use_sigmoid:
+            raise NotImplementedError("use_sigmoid=True is not on the B200 path")
+        kw, padw, sn = 4, 1, nn.utils.spectral_norm
+        seq = [sn(nn.Conv2d(input_nc, ndf, kw, 2, padw)), nn.LeakyReLU(LRELU_SLOPE, True)]
+        self._plan = [(0, 2, True)]                          # (index in model, stride, LeakyReLU follows)
+        nf = 1
+        for n in range(1, n_layers):
+            nf_prev, nf = nf, min(2 ** n, 8)
+            self._plan.append((len(seq), 2, True))
+            seq += [sn(nn.Conv2d(ndf * nf_prev, ndf * nf, kw, 2, padw, bias=False)), nn.LeakyReLU(LRELU_SLOPE, True)]
+        nf_prev, nf = nf, min(2 ** n_layers, 8)
+        self._plan.append((len(seq), 1, True))
+        seq += [sn(nn.Conv2d(ndf * nf_prev, ndf * nf, kw, 1, padw, bias=False)), nn.LeakyReLU(LRELU_SLOPE, True)]
+        self._plan.append((len(seq), 1, False))
+        seq += [sn(nn.Conv2d(ndf * nf, 1, kw, 1, padw))]
+        self.model = nn.Sequential(*seq)
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise NeuroclearError("NLayerDiscriminatorSN (B200): input is on the CPU; there is no CPU fallback")
+        x = input.float()
+        for idx, stride, lrelu in self._plan:
+            conv = self.model[idx]
+            for hook in conv._forward_pre_hooks.values():     # SpectralNorm: power iteration, weight = W / sigma
+                hook(conv, (x,))
+            x = _Conv2dK4.apply(x, conv.weight, conv.bias, stride, LRELU_SLOPE if lrelu else 1.0)
+        return x
+
+
 def define_D(input_nc, ndf, netD, n_layers_D=3, norm="batch", init_type="normal", init_gain=0.02, use_sigmoid=False,
              gpu_ids=[], dimension=3):
-    """reference networks.py:199-247; 'basic' and 'n_layers' (the PatchGAN) are provided."""
+    """reference networks.py:199-247; 'basic' / 'n_layers' (the PatchGAN) and their spectral-norm variants."""
     norm_layer = get_norm_layer(norm_type=norm, dimension=dimension)
     if netD == "basic":
         net = NLayerDiscriminator(input_nc, ndf, 3, norm_layer, use_sigmoid, dimension)
     elif netD == "n_layers":
         net = NLayerDiscriminator(input_nc, ndf, n_layers_D, norm_layer, use_sigmoid, dimension)
+    elif netD == "basic_SN":
+        net = NLayerDiscriminatorSN(input_nc, ndf, 3, norm_layer, use_sigmoid, dimension)
+    elif netD == "n_layers_SN":
+        net = NLayerDiscriminatorSN(input_nc, ndf, n_layers_D, norm_layer, use_sigmoid, dimension)
     else:
         raise NotImplementedError("Discriminator model name [%s] is not on the B200 path" % netD)
     return init_net(net, init_type, init_gain, gpu_ids)

@@ -413,6 +413,82 @@ def golden_unet_vanilla():
     np.savez_compressed(os.path.join(GOLD, "unet_vanilla_small.npz"), **out)
 
 
+def _sample(t):          # every 61st element; small tensors (<= 4096 elements) in full
+    flat = t.detach().numpy().reshape(-1)
+    return (flat if flat.size <= 4096 else flat[::GRAD_SAMPLE_STRIDE]).copy()
+
+
+def golden_sibling_models():
+    """SURVEY.md §8 f4 — one full optimize_parameters() of the REFERENCE's sibling models on a 32^3 crop (CPU fp32,
+    seeded weights): AxialToLateralGANAthenaModel (six per-slice discriminators) and AxialToLateralGANDryopsModel (the
+    ablation without G_B / D_B); and the spectral-norm PatchGAN (define_D 'basic_SN') forward + backward."""
+    rh.install()
+    from models.axial_to_lateral_gan_athena_model import AxialToLateralGANAthenaModel
+    from models.axial_to_lateral_gan_dryops_model import AxialToLateralGANDryopsModel
+    from models import networks
+    from oracle import deeplinear
+    real = torch.rand((1, 1, 32, 32, 32), generator=torch.Generator().manual_seed(7))
+    # ---- athena
+    with redirect_stdout(io.StringIO()):
+        m = AxialToLateralGANAthenaModel(apollo_opt(conversion_plane=["yz", "xy"], pool_size=50))
+    names = ["D_A_yz", "D_A_xy", "D_A_xz", "D_B_yz", "D_B_xy", "D_B_xz"]
+    m.netG_A.load_state_dict(unet.random_state_dict(seed=21, bias_std=0.05))
+    m.netG_B.load_state_dict(deeplinear.random_state_dict(seed=22))
+    for i, n in enumerate(names):
+        getattr(m, "net" + n).load_state_dict(discriminator.random_state_dict(seed=40 + i))
+    m.set_input({"A": real, "A_paths": "golden"})
+    m.optimize_parameters()
+    out = {"real": real.numpy()}
+    for k in m.loss_names:
+        out["loss_" + k] = np.array(float(getattr(m, "loss_" + k)))
+    for n in ["G_A", "G_B"] + names:
+        for k, prm in getattr(m, "net" + n).named_parameters():
+            out["after_%s.%s" % (n, k)] = _sample(prm)
+            if n.startswith("G_"):
+                out["grad_%s.%s" % (n, k)] = _sample(prm.grad)
+    np.savez_compressed(os.path.join(GOLD, "athena_step_32.npz"), **out)
+    # ---- dryops
+    with redirect_stdout(io.StringIO()):
+        m = AxialToLateralGANDryopsModel(apollo_opt())
+    m.netG_A.load_state_dict(unet.random_state_dict(seed=21, bias_std=0.05))
+    for i, n in enumerate(["D_A_axial", "D_A_lateral"]):
+        getattr(m, "net" + n).load_state_dict(discriminator.random_state_dict(seed=30 + i))
+    np.random.seed(3)
+    m.set_input({"A": real, "A_paths": "golden"})
+    m.optimize_parameters()
+    out = {"real": real.numpy(), "depth": np.array(m.projection_depth)}
+    for k in m.loss_names:
+        out["loss_" + k] = np.array(float(getattr(m, "loss_" + k)))
+    for n in ["G_A", "D_A_axial", "D_A_lateral"]:
+        for k, prm in getattr(m, "net" + n).named_parameters():
+            out["after_%s.%s" % (n, k)] = _sample(prm)
+            if n == "G_A":
+                out["grad_%s.%s" % (n, k)] = _sample(prm.grad)
+    np.savez_compressed(os.path.join(GOLD, "dryops_step_32.npz"), **out)
+    # ---- spectral-norm PatchGAN: initial state (incl. the power-iteration vectors), one training-mode forward+backward
+    torch.manual_seed(77)
+    with redirect_stdout(io.StringIO()):
+        net = networks.define_D(1, 64, "basic_SN", norm="instance", use_sigmoid=False, init_type="kaiming",
+                                init_gain=0.02, gpu_ids=[], dimension=2)
+    # the initial state is a function of the seed alone (same torch modules built in the same order on both sides):
+    # the fixture keeps per-tensor float64 sums as its checksum instead of 11 MB of weights
+    out = {"sdsum_" + k: np.array(float(v.double().sum())) for k, v in net.state_dict().items()}
+    x = torch.rand((2, 1, 44, 36), generator=torch.Generator().manual_seed(2)).requires_grad_(True)
+    net.train()
+    pred = net(x)
+    crit = networks.GANLoss("lsgan")
+    loss = crit(pred, True) * 0.5 + crit(pred, False) * 0.25
+    loss.backward()
+    out.update({"x": x.detach().numpy(), "pred": pred.detach().numpy(), "loss": np.array(float(loss)),
+                "dx": x.grad.numpy()})
+    for k, prm in net.named_parameters():
+        out["grad_" + k] = prm.grad.numpy().reshape(-1)[::7].copy()
+    for k, v in net.state_dict().items():
+        if k.endswith(("_u", "_v")):
+            out["after_" + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "discriminator_sn_44x36.npz"), **out)
+
+
 def golden_report():
     """The PSNR report of test_dice.py:239-253 computed with the REFERENCE's util.util functions (normalize,
     standardize, get_psnr) on three small uint16 volumes, and the oracle's restatement checked against it."""
@@ -454,6 +530,7 @@ def main():
     golden_augment()
     golden_report()
     golden_unet_vanilla()
+    golden_sibling_models()
     print("golden vectors written to", GOLD)
 
 
