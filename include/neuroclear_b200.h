@@ -342,6 +342,12 @@ int nc_amax_axis(const void* vol, int32_t elem_bytes, int32_t z, int32_t y, int3
  * params4 = {mean, std, standardized minimum, 255 / (standardized max - min)}; sum of squared differences of two
  * uint8 volumes (an exact integer). */
 int nc_volume_moments(const void* vol, int32_t elem_bytes, int64_t n, uint64_t* out4, nc_stream_t stream);
+/* sum over voxels of (double(v) - mean)^2 in numpy's pairwise association order (what np.std computes: the last bit
+ * of this float64 sum decides the reference's double-normalised uint8 volumes).  scratch:
+ * nc_pairwise_sqdev_scratch_doubles(n) doubles; out1: one double. */
+int64_t nc_pairwise_sqdev_scratch_doubles(int64_t n);
+int nc_pairwise_sqdev_sum(const void* vol, int32_t elem_bytes, int64_t n, double mean, double* scratch, double* out1,
+                          nc_stream_t stream);
 int nc_standardize_normalize_u8(const void* vol, int32_t elem_bytes, int64_t n, const double* params4, uint8_t* out,
                                 nc_stream_t stream);
 int nc_sqdiff_u8(const uint8_t* a, const uint8_t* b, int64_t n, uint64_t* out1, nc_stream_t stream);

@@ -85,6 +85,8 @@ SIGNATURES = {
     "nc_blend_gather_f64": (C.c_int, [vp, vp, vp, I3, I3, i32, i32, i32, i32, vp, vp]),
     "nc_amax_axis": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "nc_volume_moments": (C.c_int, [vp, i32, i64, vp, vp]),
+    "nc_pairwise_sqdev_scratch_doubles": (i64, [i64]),
+    "nc_pairwise_sqdev_sum": (C.c_int, [vp, i32, i64, f64, vp, vp, vp]),
     "nc_standardize_normalize_u8": (C.c_int, [vp, i32, i64, vp, vp, vp]),
     "nc_sqdiff_u8": (C.c_int, [vp, vp, i64, vp, vp]),
 }

@@ -171,6 +171,76 @@ moments_kernel(const T* __restrict__ v, long long n, unsigned long long* __restr
   }
 }
 
+// np.std's sum: numpy/core/src/umath/loops_utils.h.src::pairwise_sum over x_i = (double(v_i) - mean)^2, reproduced in
+// numpy's exact association order (np.std of the whole volume = one contiguous float64 reduction of n elements):
+//   n < 8: sequential;  n <= 128: eight interleaved accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail;
+//   else split at n2 = n/2 - (n/2) % 8 and add the two halves.
+// The reference's double normalisation (test_dice.py:243-249) puts every voxel of its second pass exactly on an
+// integer boundary of the truncating uint8 cast, so the LAST BIT of this sum decides the volume: any other summation
+// order changes ~half of the voxels by one grey level.  Thread t owns the depth-`depth` node of that tree (>= 2048
+// elements), evaluates it serially in numpy's order, and one block then folds the 2^depth partial sums pairwise.
+template <typename T>
+__device__ double pw_leaf(const T* __restrict__ v, long long off, int n, double mean) {
+  auto X = [&](long long i) {
+    const double d = __dsub_rn(static_cast<double>(v[off + i]), mean);
+    return __dmul_rn(d, d);
+  };
+  if (n < 8) {
+    double res = -0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, X(i));
+    return res;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = X(j);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], X(i + j));
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, X(i));
+  return res;
+}
+template <typename T>
+__device__ double pw_node(const T* __restrict__ v, long long off, long long n, double mean) {
+  if (n <= 128) return pw_leaf(v, off, static_cast<int>(n), mean);
+  long long n2 = n / 2;
+  n2 -= n2 % 8;
+  const double a = pw_node(v, off, n2, mean);
+  const double b = pw_node(v, off + n2, n - n2, mean);
+  return __dadd_rn(a, b);
+}
+template <typename T>
+__global__ void __launch_bounds__(128)
+pairwise_sqdev_kernel(const T* __restrict__ v, long long n, double mean, int depth, double* __restrict__ partial) {
+  const long long t = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  if (t >= (1ll << depth)) return;
+  long long off = 0, len = n;
+  for (int b = depth - 1; b >= 0; --b) {
+    long long n2 = len / 2;
+    n2 -= n2 % 8;
+    if ((t >> b) & 1) off += n2, len -= n2; else len = n2;
+  }
+  partial[t] = pw_node(v, off, len, mean);
+}
+__global__ void __launch_bounds__(1024) pairwise_fold_kernel(double* __restrict__ partial, int depth, double* out) {
+  for (int lv = depth - 1; lv >= 0; --lv) {       // in place: node j of level lv = children 2j, 2j+1 of level lv+1
+    const long long cnt = 1ll << lv;
+    // read both children before anyone overwrites them: two phases per level
+    for (long long base = 0; base < cnt; base += 1024) {
+      const long long j = base + threadIdx.x;
+      double s = 0.0;
+      if (j < cnt) s = __dadd_rn(partial[2 * j], partial[2 * j + 1]);
+      __syncthreads();
+      if (j < cnt) partial[j] = s;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) out[0] = partial[0];
+}
+
 // util.normalize(util.standardize(v), np.uint8) (util/util.py:56-71,107-108) per voxel, float64 as numpy evaluates it:
 //   s = (v - mean) / std;  out = uint8((s - s_min) * (255 / (s_max - s_min)) + 0)       (truncation)
 // p = {mean, std, s_min, scale}; the four scalars come from the exact moments (host side, float64).
@@ -277,6 +347,34 @@ int nc_volume_moments(const void* vol, int32_t elem_bytes, int64_t n, uint64_t* 
   else
     moments_kernel<uint8_t><<<blocks, 256, 0, S(stream)>>>(static_cast<const uint8_t*>(vol), n,
                                                            reinterpret_cast<unsigned long long*>(out4));
+  NC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t nc_pairwise_sqdev_scratch_doubles(int64_t n) {
+  int depth = 0;
+  while ((n >> (depth + 1)) >= 2048) ++depth;
+  return 1ll << depth;
+}
+
+int nc_pairwise_sqdev_sum(const void* vol, int32_t elem_bytes, int64_t n, double mean, double* scratch, double* out1,
+                          nc_stream_t stream) {
+  if (elem_bytes != 1 && elem_bytes != 2) return set_error("pairwise_sqdev_sum: uint8 / uint16 volumes only");
+  if (n <= 0) return set_error("pairwise_sqdev_sum: empty volume");
+  int depth = 0;
+  while ((n >> (depth + 1)) >= 2048) ++depth;      // every node above `depth` has > 128 elements: internal in numpy
+  static bool once[64] = {false};
+  if (first_use_on_device(once)) NC_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+  const long long threads = 1ll << depth;
+  const unsigned blocks = static_cast<unsigned>((threads + 127) / 128);
+  if (elem_bytes == 2)
+    pairwise_sqdev_kernel<uint16_t><<<blocks, 128, 0, S(stream)>>>(static_cast<const uint16_t*>(vol), n, mean, depth,
+                                                                   scratch);
+  else
+    pairwise_sqdev_kernel<uint8_t><<<blocks, 128, 0, S(stream)>>>(static_cast<const uint8_t*>(vol), n, mean, depth,
+                                                                  scratch);
+  NC_CUDA(cudaGetLastError());
+  pairwise_fold_kernel<<<1, 1024, 0, S(stream)>>>(scratch, depth, out1);
   NC_CUDA(cudaGetLastError());
   return 0;
 }

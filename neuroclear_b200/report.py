@@ -64,15 +64,20 @@ def _moments(v):
 
 
 def standardize_normalize_u8(v: torch.Tensor) -> torch.Tensor:
-    """util.normalize(util.standardize(v), data_type=np.uint8) on the device.  mean and std are the correctly rounded
-    float64 values of the exact integer moments (numpy's pairwise float64 sums agree to a few ulp)."""
+    """util.normalize(util.standardize(v), data_type=np.uint8) on the device, bit for bit: the mean is exact (integer
+    sum / n, as numpy's: sums of integers are exact in float64), the standard deviation reproduces np.std's float64
+    pairwise summation order (nc_pairwise_sqdev_sum) — its last bit decides the second normalisation pass of
+    test_dice.py:243-249, where every voxel sits on an integer boundary of the truncating cast."""
+    from . import _lib
     with torch.cuda.device(v.device):
         n, s, q, mn, mx = _moments(v)
-        mean = s / n                                            # correctly rounded big-int division
-        var_num = n * q - s * s                                 # exact: n^2 * variance
-        if var_num <= 0:
+        mean = s / n                                            # correctly rounded; == np.mean(v)
+        if n * q - s * s <= 0:
             raise NeuroclearError("standardize: constant volume (the reference divides by zero)")
-        std = math.sqrt(var_num / (n * n))
+        scratch = torch.empty(_lib.load().nc_pairwise_sqdev_scratch_doubles(n), dtype=torch.float64, device=v.device)
+        acc = torch.empty(1, dtype=torch.float64, device=v.device)
+        call("nc_pairwise_sqdev_sum", ptr(v), v.element_size(), i64(n), mean, ptr(scratch), ptr(acc), stream_ptr())
+        std = math.sqrt(float(acc.item()) / n)                  # == np.std(v)
         smin, smax = (mn - mean) / std, (mx - mean) / std       # standardisation is monotone
         scale = (255 - 0) / (smax - smin)
         params = torch.tensor([mean, std, smin, scale], dtype=torch.float64).to(v.device)

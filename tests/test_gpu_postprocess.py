@@ -94,16 +94,28 @@ def test_save_projections_bit_exact(cuda):
 def test_psnr_report_matches_reference_fixture(cuda, tmp_path):
     from neuroclear_b200 import report
     z = np.load(os.path.join(GOLDEN, "report_psnr.npz"))
-    # The reference normalises twice; the second pass maps a uint8 volume that already spans 0..255 onto itself in
-    # exact arithmetic, so its truncating cast sits EXACTLY on integer boundaries and every voxel is decided by the
-    # last bit of np.std's float64 pairwise sum (order-dependent).  The device uses the correctly rounded standard
-    # deviation of the exact integer moments instead: the uint8 volumes agree to 1 LSB, the PSNR to a few 1e-2 dB.
+    # The reference normalises twice; its second pass maps a uint8 volume that already spans 0..255 onto itself, so
+    # every voxel sits EXACTLY on an integer boundary of the truncating cast and the last bit of np.std's float64
+    # pairwise sum decides it.  nc_pairwise_sqdev_sum reproduces numpy's association order: everything is bit-exact.
     for name in ("real", "fake", "gt"):
         d = torch.from_numpy(z[name]).to(cuda)
-        once = report.standardize_normalize_u8(d)
-        got8 = report.standardize_normalize_u8(once).cpu().numpy()
-        diff = np.abs(got8.astype(np.int16) - z[name + "8"].astype(np.int16))
-        assert diff.max() <= 1, name
+        got8 = report.standardize_normalize_u8(report.standardize_normalize_u8(d)).cpu().numpy()
+        assert np.array_equal(got8, z[name + "8"]), name
     p_in, p_out, msg = report.psnr_report(z["real"], z["fake"], z["gt"], cuda, name="exp", web_dir=str(tmp_path))
-    assert abs(p_in - float(z["psnr_input_gt"])) <= 0.1 and abs(p_out - float(z["psnr_output_gt"])) <= 0.1
+    assert p_in == float(z["psnr_input_gt"]) and p_out == float(z["psnr_output_gt"])
     assert "(psnr: %.4f)" % p_out in msg and (tmp_path / "metrics.txt").read_text().startswith("Experiment Name: exp")
+
+
+@pytest.mark.parametrize("shape,dtype", [((7, 9, 11), np.uint16), ((64, 72, 80), np.uint16), ((33, 47, 51), np.uint8),
+                                         ((150, 200, 210), np.uint16), ((1, 1, 5), np.uint8)])
+def test_std_reproduces_numpy_pairwise_sum_bit_for_bit(cuda, shape, dtype):
+    from neuroclear_b200 import _lib
+    from neuroclear_b200._lib import call, i64, ptr, stream_ptr
+    v = np.random.default_rng(shape[0]).integers(0, np.iinfo(dtype).max + 1, shape).astype(dtype)
+    d = torch.from_numpy(v).to(cuda)
+    n = v.size
+    mean = float(np.mean(v))
+    scratch = torch.empty(_lib.load().nc_pairwise_sqdev_scratch_doubles(n), dtype=torch.float64, device=cuda)
+    acc = torch.empty(1, dtype=torch.float64, device=cuda)
+    call("nc_pairwise_sqdev_sum", ptr(d), d.element_size(), i64(n), mean, ptr(scratch), ptr(acc), stream_ptr())
+    assert np.sqrt(float(acc.item()) / n) == float(np.std(v))
