@@ -40,6 +40,9 @@ int nc_device_sm_count(void);
 /* test hook: cap the persistent grid of the tensor-core conv kernels at n CTAs (0 = one per SM) so that small test
  * problems also exercise the several-tiles-per-CTA path (ring wrap-around, accumulator ping-pong) */
 void nc_debug_set_max_ctas(int32_t n);
+/* test / measurement hook: 0 disables the remainder-pair kernel of the N-tile-128 k3 convolutions (the last, partly
+ * filled 16-line h-tile is then computed by the regular kernel); the stored values are identical either way */
+void nc_debug_set_remainder_pairs(int32_t on);
 
 /* ---- dicing geometry (host-only integer math) --------------------------------------------------------------
  * util/util.py:196-215 pad_for_dicing  +  data/diceImage_dataset.py:82-106 DiceCube.__init__/indexToCoordinates

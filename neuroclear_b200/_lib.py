@@ -22,6 +22,7 @@ SIGNATURES = {
     "nc_build_source_hash": (C.c_char_p, []),
     "nc_device_sm_count": (C.c_int, []),
     "nc_debug_set_max_ctas": (None, [i32]),
+    "nc_debug_set_remainder_pairs": (None, [i32]),
     "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),
     "nc_dice_extract_u16": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),
     "nc_dice_extract_u8": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),

@@ -18,6 +18,7 @@ const char* nc_last_error(void) { return last_error(); }
 const char* nc_build_source_hash(void) { return "NC_SOURCE_HASH=" NC_SOURCE_HASH; }
 
 void nc_debug_set_max_ctas(int32_t n) { debug_set_max_ctas(n); }
+void nc_debug_set_remainder_pairs(int32_t on) { debug_set_remainder_pairs(on); }
 
 int nc_device_sm_count(void) {
   int dev = 0, n = 0;

@@ -88,6 +88,9 @@ struct ConvTcArgs {
   int n_tiles;  // GEMM N / BN
   int tiles_w, tiles_h, tiles_d;
   int total_tiles;
+  int tiles_h_cap;   // > 0: the regular kernel covers only this many 16-line h-tiles (the rest is the RP kernel's)
+  int rp_h0, rp_rem;  // remainder-pair kernel: first line and number of lines (1..6) of the remainder strip
+  int stats_tile0;    // remainder-pair kernel: first row of its tiles in stats_partial
   const uint8_t* wpacked;
   // MODE 0
   __half* out_raw;       // [NB][D][H][W][ldo] raw conv output, fp16
@@ -617,6 +620,334 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------ remainder pairs
+// Tile quantisation in h.  The MMA's 128 rows are 16 eight-row groups one halo LINE apart, i.e. 16 h-lines of 8 voxels;
+// a plane of H = 16 q + R lines costs q + 1 h-tiles, the last one with only R useful lines (70^3: 6 of 16, 35^3: 3 of
+// 16 — 17.6 % / 61 % more MMA rows than voxels over those levels).  For R <= 6 the remainder strip of TWO consecutive
+// d-planes fits ONE accumulator: the strip of plane d is staged as a box of 8 lines (R <= 6 output lines + 2 halo
+// lines), the boxes of planes d-1, d, d+1, ... are laid back to back in shared memory, and because a box is exactly 8
+// lines = half of the 16 groups, a 16-line window starting at line (kd * 8 + kh) of that chain reads
+//     groups 0..7  -> plane d   + kd - 1, lines h0 - 1 + kh ..      groups 8..15 -> plane d+1 + kd - 1, same lines
+// with the SAME uniform group stride the regular kernel uses.  Groups 6, 7 / 14, 15 compute rows nobody stores.  One
+// tile = 2 accumulators = 4 output planes fed by a chain of 6 boxes (60 KB per 64-channel chunk, double buffered);
+// weights, K order (chunk, kd, kh, kw), epilogue arithmetic and statistics are those of the regular kernel, so every
+// stored value is bit-identical to what the 16-line tile would have produced.  70^3: 20 -> 18 MMA tiles per four
+// planes, 35^3: 12 -> 10.
+template <int BN>
+struct RpCfg {
+  static constexpr int LINES = 8;
+  static constexpr int HALO_W = TW + 2;
+  static constexpr int BOX_ROWS = LINES * HALO_W;
+  static constexpr int BOX_BYTES = BOX_ROWS * 128;  // 10240: a multiple of the 1 KB swizzle atom
+  static constexpr int NACC = 2;                    // accumulators per tile
+  static constexpr int PLANES = 2 * NACC;           // output planes per tile
+  static constexpr int NBOX = PLANES + 2;
+  static constexpr int CHAIN_BYTES = NBOX * BOX_BYTES;
+  static constexpr int NCHAIN = 2;
+  static constexpr int BSTAGE_BYTES = BN * 128;
+  static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4;
+  static constexpr int SMEM_LIMIT = 232448;
+  static constexpr int NBST_FIT = (SMEM_LIMIT - 1024 - AUX_BYTES - NCHAIN * CHAIN_BYTES) / BSTAGE_BYTES;
+  static constexpr int NBST = NBST_FIT > 8 ? 8 : NBST_FIT;
+  static constexpr int ACC_COLS = NACC * BN;
+  static constexpr int TMEM_COLS = pow2_at_least(2 * ACC_COLS);
+  // the last window over-reads 2 lines past its chain (rows nobody stores): chain 1 is followed by the weight ring
+  static constexpr int SMEM_BYTES = 1024 + NCHAIN * CHAIN_BYTES + NBST * BSTAGE_BYTES + AUX_BYTES;
+  static_assert(BOX_BYTES % 1024 == 0, "boxes must keep the swizzle phase");
+  static_assert(NBST >= 2 && 2 * ACC_COLS <= 512, "RP configuration does not fit");
+};
+
+struct RpCoord {
+  int n_tile, nb, d0, w0, spatial;
+};
+__device__ __forceinline__ RpCoord decode_rp(const ConvTcArgs& a, int tile) {
+  RpCoord t;
+  const int per_n = a.NB * a.tiles_d * a.tiles_w;
+  t.n_tile = tile / per_n;
+  int r = tile - t.n_tile * per_n;
+  t.spatial = r;
+  const int wt = r % a.tiles_w;
+  r /= a.tiles_w;
+  const int dt = r % a.tiles_d;
+  t.nb = r / a.tiles_d;
+  t.w0 = wt * TW;
+  t.d0 = dt * 4;
+  return t;
+}
+
+template <int BN, bool XF>
+__global__ void __launch_bounds__(XF ? 384 : 256, 1)
+conv3d_rp_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs args) {
+  using C = RpCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + C::NCHAIN * C::CHAIN_BYTES;
+  uint8_t* aux = smB + C::NBST * C::BSTAGE_BYTES;
+  uint64_t* chainFull = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* chainEmpty = chainFull + C::NCHAIN;
+  uint64_t* chainReady = chainEmpty + C::NCHAIN;  // XF only
+  uint64_t* bFull = chainReady + C::NCHAIN;
+  uint64_t* bEmpty = bFull + C::NBST;
+  uint64_t* accFull = bEmpty + C::NBST;
+  uint64_t* accEmpty = accFull + 2;
+  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(accEmpty + 2);
+  float* statScratch = reinterpret_cast<float*>(aux + 1024);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmapA);
+    for (int i = 0; i < C::NCHAIN; ++i) {
+      ptx::mbar_init(&chainFull[i], 1);
+      ptx::mbar_init(&chainEmpty[i], 1);
+      ptx::mbar_init(&chainReady[i], 1);
+    }
+    for (int i = 0; i < C::NBST; ++i) {
+      ptx::mbar_init(&bFull[i], 1);
+      ptx::mbar_init(&bEmpty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&accFull[i], 1);
+      ptx::mbar_init(&accEmpty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<C::TMEM_COLS>(tmemPtr);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmemPtr;
+  const int first_tile = blockIdx.x, tile_stride = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ chain producer: 6 boxes of 8 lines per chunk
+    if (lane == 0) {
+      int cb = 0;
+      uint32_t ph = 0;
+      for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
+        const RpCoord t = decode_rp(args, tile);
+        for (int c = 0; c < args.chunks; ++c) {
+          ptx::mbar_wait(&chainEmpty[cb], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&chainFull[cb], C::CHAIN_BYTES);
+          for (int b = 0; b < C::NBOX; ++b)
+            ptx::tma_load_5d(smA + cb * C::CHAIN_BYTES + b * C::BOX_BYTES, &tmapA, &chainFull[cb], c * 64, t.w0 - 1,
+                             args.rp_h0 - 1, t.d0 - 1 + b, t.nb);
+          if (++cb == C::NCHAIN) {
+            cb = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ weight-stage producer (the regular packed image)
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
+        const RpCoord t = decode_rp(args, tile);
+        const uint8_t* wsrc = args.wpacked + static_cast<size_t>(t.n_tile) * args.chunks * 27 * C::BSTAGE_BYTES;
+        const int nst = args.chunks * 27;
+        for (int s = 0; s < nst; ++s) {
+          ptx::mbar_wait(&bEmpty[st], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&bFull[st], C::BSTAGE_BYTES);
+          ptx::bulk_load(smB + st * C::BSTAGE_BYTES, wsrc + static_cast<size_t>(s) * C::BSTAGE_BYTES, C::BSTAGE_BYTES,
+                         &bFull[st]);
+          if (++st == C::NBST) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loops, one elected lane)
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN);
+    constexpr uint32_t A_HI = ((C::HALO_W * 128u) >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t LO_FLAGS = 1u << 16;
+    const uint32_t smA_u32 = ptx::smem_u32(smA);
+    const uint32_t smB_u32 = ptx::smem_u32(smB);
+    int cb = 0, bst = 0, it = 0;
+    uint32_t cph = 0, bph = 0;
+    for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      ptx::mbar_wait(&accEmpty[buf], (use & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * C::ACC_COLS;
+      for (int c = 0; c < args.chunks; ++c) {
+        ptx::mbar_wait(XF ? &chainReady[cb] : &chainFull[cb], cph);
+        ptx::tc_fence_after();
+        const uint32_t chain = smA_u32 + cb * C::CHAIN_BYTES;
+        for (int kd = 0; kd < 3; ++kd) {
+          for (int khw = 0; khw < 9; ++khw) {
+            const int kh = khw / 3, kw = khw - kh * 3;
+            ptx::mbar_wait(&bFull[bst], bph);
+            ptx::tc_fence_after();
+            const uint32_t b_lo = (((smB_u32 + bst * C::BSTAGE_BYTES) >> 4) & 0x3FFF) | LO_FLAGS;
+            const uint32_t first = (c == 0 && kd == 0 && khw == 0) ? 0u : 1u;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int j = 0; j < C::NACC; ++j) {
+                const uint32_t a_addr = chain + (((2 * j + kd) * C::LINES + kh) * C::HALO_W + kw) * 128;
+                const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | LO_FLAGS;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16(acc0 + j * BN, (static_cast<uint64_t>(A_HI) << 32) | (a_lo + 2 * k),
+                                (static_cast<uint64_t>(B_HI) << 32) | (b_lo + 2 * k), idesc, (k == 0) ? first : 1u);
+              }
+              ptx::umma_commit(&bEmpty[bst]);
+              if (kd == 2 && khw == 8) {
+                ptx::umma_commit(&chainEmpty[cb]);
+                if (c == args.chunks - 1) ptx::umma_commit(&accFull[buf]);
+              }
+            }
+            __syncwarp();
+            if (++bst == C::NBST) {
+              bst = 0;
+              bph ^= 1;
+            }
+          }
+        }
+        if (++cb == C::NCHAIN) {
+          cb = 0;
+          cph ^= 1;
+        }
+      }
+    }
+  } else if (XF && warp >= 8) {
+    // ------------------------------------------------------------ in-place InstanceNorm + ReLU of the landed chain
+    const int tt = threadIdx.x - 256;
+    const int g = tt & 7;
+    const int r0 = tt >> 3;
+    int cb = 0;
+    uint32_t ph = 0;
+    for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride) {
+      const RpCoord t = decode_rp(args, tile);
+      for (int c = 0; c < args.chunks; ++c) {
+        float mu[8], rs[8];
+        const float* mr = args.in_mr + static_cast<size_t>(t.nb) * 2 * args.cin_total + c * 64 + g * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          mu[i] = __ldg(mr + i);
+          rs[i] = __ldg(mr + args.cin_total + i);
+        }
+        ptx::mbar_wait(&chainFull[cb], ph);
+        uint8_t* ch = smA + cb * C::CHAIN_BYTES;
+#pragma unroll 2
+        for (int row = r0; row < C::NBOX * C::BOX_ROWS; row += 16) {
+          const int b = row / C::BOX_ROWS, rb = row - b * C::BOX_ROWS;
+          const int line = rb / C::HALO_W, ww = rb - line * C::HALO_W;
+          const int d = t.d0 - 1 + b, h = args.rp_h0 - 1 + line, w = t.w0 - 1 + ww;
+          if (d >= 0 && d < args.D && h >= 0 && h < args.H && w >= 0 && w < args.W) {
+            uint4* p = reinterpret_cast<uint4*>(ch + row * 128 + ((g ^ (row & 7)) << 4));
+            uint4 v = *p;
+            __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h2[e]);
+              h2[e] = __floats2half2_rn(fmaxf((f.x - mu[2 * e]) * rs[2 * e], 0.f),
+                                        fmaxf((f.y - mu[2 * e + 1]) * rs[2 * e + 1], 0.f));
+            }
+            *p = v;
+          }
+        }
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(4, 128);
+        if (tt == 0) ptx::mbar_arrive(&chainReady[cb]);
+        if (++cb == C::NCHAIN) {
+          cb = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------ epilogue: raw fp16 store + statistics partials
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int mw = m & 7, grp = m >> 3;
+    const int pl = grp >> 3, line = grp & 7;  // pl is warp-uniform (= q >> 1)
+    int it = 0;
+    for (int tile = first_tile; tile < args.total_tiles; tile += tile_stride, ++it) {
+      const RpCoord t = decode_rp(args, tile);
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      ptx::mbar_wait(&accFull[buf], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * C::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      const int w = t.w0 + mw, h = args.rp_h0 + line;
+      const bool valid_hw = (w < args.W) && (line < args.rp_rem);
+      float csum[BN / 32], csq[BN / 32];
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) csum[cc] = csq[cc] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < C::NACC; ++j) {
+        if (t.d0 + 2 * j >= args.D) break;  // CTA-uniform
+        const int d = t.d0 + 2 * j + pl;
+        const bool valid = valid_hw && d < args.D;
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t raw[32];
+          ptx::tmem_ld32(acc0 + j * BN + cc * 32, raw);
+          ptx::tmem_ld_wait();
+          const int co = t.n_tile * BN + cc * 32;
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(
+                args.out_raw + (((static_cast<size_t>(t.nb) * args.D + d) * args.H + h) * args.W + w) * args.ldo + co);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_half2_sat(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
+                                  pack_half2_sat(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
+                                  pack_half2_sat(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
+                                  pack_half2_sat(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
+          }
+          float v[32], v2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = valid ? __uint_as_float(raw[i]) : 0.f;
+            v[i] = x;
+            v2[i] = x * x;
+          }
+          csum[cc] += warp_colsum32(v, lane);
+          csq[cc] += warp_colsum32(v2, lane);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&accEmpty[buf]);
+
+      float* mine = statScratch + q * 2 * BN;
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        mine[cc * 32 + lane] = csum[cc];
+        mine[BN + cc * 32 + lane] = csq[cc];
+      }
+      ptx::named_bar_sync(1, 128);
+      const int e = threadIdx.x - 128;
+      for (int i = e; args.stats_partial != nullptr && i < 2 * BN; i += 128) {
+        const float s = (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
+        const int which = i / BN, col = i - which * BN;
+        args.stats_partial[(static_cast<size_t>(args.stats_tile0 + t.spatial) * 2 + which) * args.ldo +
+                           t.n_tile * BN + col] = s;
+      }
+      ptx::named_bar_sync(1, 128);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weights
 // Packed image: [n_tile][chunk][tap][row r < BN][128 B], 16-byte unit j of row r stored at unit j ^ (r & 7).
 // conv:  w is OIDHW fp32 (Cout, Cin, k, k, k); GEMM column n = output channel.
@@ -735,7 +1066,7 @@ static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream)
     tmo = tm;
   }
   a.tiles_w = (a.W + TW - 1) / TW;
-  a.tiles_h = (a.H + TH - 1) / TH;
+  a.tiles_h = a.tiles_h_cap > 0 ? a.tiles_h_cap : (a.H + TH - 1) / TH;
   a.tiles_d = (a.D + TD - 1) / TD;
   a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_h * a.tiles_w;
   a.cin_total = Cin;
@@ -750,9 +1081,48 @@ static int launch_cfg(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream)
 int conv3d_k3_bn(int Cout) { return Cout == 64 ? 64 : 128; }
 int conv3d_k3_td(int Cout) { return Cout == 64 ? 4 : 2; }
 
+// Remainder-pair kernel (see RpCfg): used by the N-tile-128 forward path when the last h-tile would hold <= 6 lines.
+static bool g_rp_enabled = true;
+void debug_set_remainder_pairs(int on) { g_rp_enabled = on != 0; }
+static inline int rp_rem(int H, int Cout) {
+  const int r = H % TH;
+  return (g_rp_enabled && Cout != 64 && r >= 1 && r <= 6) ? r : 0;
+}
+
 size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout) {
   const int td = conv3d_k3_td(Cout);
-  return static_cast<size_t>(NB) * ((D + td - 1) / td) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  const size_t tw = (W + TW - 1) / TW;
+  if (rp_rem(H, Cout))
+    return static_cast<size_t>(NB) * ((D + td - 1) / td) * (H / TH) * tw + static_cast<size_t>(NB) * ((D + 3) / 4) * tw;
+  return static_cast<size_t>(NB) * ((D + td - 1) / td) * ((H + TH - 1) / TH) * tw;
+}
+
+template <int BN>
+static int launch_rp(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
+  using C = RpCfg<BN>;
+  CUtensorMap tm;
+  if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::LINES)) return rc;
+  a.tiles_w = (a.W + TW - 1) / TW;
+  a.tiles_h = 1;
+  a.tiles_d = (a.D + 3) / 4;
+  a.total_tiles = a.n_tiles * a.NB * a.tiles_d * a.tiles_w;
+  a.cin_total = Cin;
+  const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
+  const int grid = a.total_tiles < cap ? a.total_tiles : cap;
+  static bool attr_set[2][64] = {{false}};
+  if (a.in_mr) {
+    auto kern = conv3d_rp_kernel<BN, true>;
+    if (first_use_on_device(attr_set[1]))
+      NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    kern<<<grid, 384, C::SMEM_BYTES, stream>>>(tm, a);
+  } else {
+    auto kern = conv3d_rp_kernel<BN, false>;
+    if (first_use_on_device(attr_set[0]))
+      NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, a);
+  }
+  NC_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H, int W, int Cin, const void* wpacked,
@@ -772,6 +1142,18 @@ int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H
   }
   if (Cout % 128) return set_error("conv3d_k3_fwd: Cout must be 64 or a multiple of 128");
   a.n_tiles = Cout / 128;
+  if (const int rem = rp_rem(H, Cout)) {
+    // full 16-line h-tiles by the regular kernel, the remainder strip (rem <= 6 lines) by the remainder-pair kernel
+    const int full = H / TH;
+    if (full > 0) {
+      a.tiles_h_cap = full;
+      if (int rc = launch_cfg<3, 128, 2, 0>(x, a, Cin, stream)) return rc;
+    }
+    a.tiles_h_cap = 0;
+    a.rp_h0 = full * TH, a.rp_rem = rem;
+    a.stats_tile0 = NB * ((D + 1) / 2) * full * ((W + TW - 1) / TW);
+    return launch_rp<128>(x, a, Cin, stream);
+  }
   return launch_cfg<3, 128, 2, 0>(x, a, Cin, stream);
 }
 

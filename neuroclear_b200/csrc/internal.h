@@ -31,6 +31,7 @@ TensorMapEncodeTiledFn get_tensor_map_encoder();
 
 // conv3d_tc.cu
 void debug_set_max_ctas(int n);
+void debug_set_remainder_pairs(int on);
 int conv3d_k3_bn(int Cout);
 int conv3d_k3_td(int Cout);
 size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout);

@@ -48,6 +48,9 @@ static const Case cases[] = {
     {"k3_64_128_odd", 0, 1, 3, 5, 3, 64, 128},       {"ct_128_64", 1, 1, 4, 18, 10, 128, 64},
     {"ct_256_128", 1, 2, 3, 17, 9, 256, 128},        {"k3_64_64_deep", 0, 2, 11, 17, 9, 64, 64},
     {"k3_128_64_deep", 0, 1, 9, 20, 20, 128, 64},
+    {"k3_128_128_rp6", 0, 2, 7, 22, 20, 128, 128},   {"k3_256_256_rp3", 0, 1, 9, 35, 35, 256, 256},
+    {"k3_64_128_rp_small", 0, 1, 6, 5, 9, 64, 128},  {"k3_128_128_l1", 0, 1, 8, 70, 70, 128, 128},
+    {"k3_256_256_l2", 0, 1, 35, 35, 35, 256, 256},
 };
 static const int ncases = sizeof(cases) / sizeof(cases[0]);
 
@@ -243,6 +246,7 @@ static void run_time(const Shape& s, int NB, int iters) {
 }
 
 int main(int argc, char** argv) {
+  if (getenv("NC_RP")) nc_debug_set_remainder_pairs(atoi(getenv("NC_RP")));   // 0: regular tiles only
   if (argc >= 3 && !strcmp(argv[1], "check")) {
     const int ci = atoi(argv[2]);
     const int cap = argc > 3 ? atoi(argv[3]) : 0;   // persistent-grid cap: > 0 forces several tiles per CTA

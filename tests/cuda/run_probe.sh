@@ -8,7 +8,7 @@ LOG=gpurun_out/probe.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $LOG 2>&1
 P=build/probe_conv
 for cap in 0 2; do
-  for c in 0 1 2 3 4 5 6 7 8; do
+  for c in 0 1 2 3 4 5 6 7 8 9 10 11; do
     timeout 120 $P check $c $cap >> $LOG 2>&1 || echo "case $c cap $cap exit=$?" >> $LOG
   done
 done

@@ -60,12 +60,21 @@ def test_reference_train_onecube_script_runs_on_the_b200_path(tmp_path, cuda):
     """Two iterations of train_onecube.py --model axial_to_lateral_gan_apollo: the reference's model class, options,
     loop and torch.optim.Adam, on our generators / discriminators / Volume / GPU data pipeline.  Same seeds in both
     runs; the data pipeline is bit-exact, so both runs see the same crops; the 11 losses of iteration 1 must agree
-    within 2 % (weights are the seeded init_weights draw of each run: identical)."""
+    within 2 % (both runs load the same six checkpoints through the reference's --continue_train)."""
     from neuroclear_b200 import volume_io
+    from oracle import apollo_step, deeplinear, discriminator, unet as ounet
     vol = (np.random.default_rng(1).random((40, 72, 72)) ** 2 * 65535).astype(np.uint16)
     data = tmp_path / "data"
     data.mkdir()
     volume_io.write_volume(str(data / "volume.tif"), vol)
+    # both runs start from the same checkpoints (--continue_train): init_weights draws differ between CPU and CUDA RNGs
+    ckpt = tmp_path / "ckpt" / "exp"
+    ckpt.mkdir(parents=True)
+    sds = {"G_A": ounet.random_state_dict(seed=21, bias_std=0.05), "G_B": deeplinear.random_state_dict(seed=22)}
+    for i, n in enumerate(apollo_step.D_NAMES):
+        sds[n] = discriminator.random_state_dict(seed=30 + i)
+    for n, sd in sds.items():
+        torch.save(sd, str(ckpt / ("latest_net_%s.pth" % n)))
     common = ["--dataroot", str(data), "--name", "exp", "--checkpoints_dir", str(tmp_path / "ckpt"),
               "--model", "axial_to_lateral_gan_apollo", "--netG", "unet_deconv", "--netG_B", "deep_linear_gen",
               "--netD", "basic", "--norm", "instance", "--no_dropout", "--init_type", "kaiming", "--gan_mode", "lsgan",

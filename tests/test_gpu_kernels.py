@@ -170,7 +170,9 @@ def test_first_layer_conv_and_stats(cuda, lib):
 
 
 @pytest.mark.parametrize("cin,cout,nb,d,h,w", [(64, 64, 1, 7, 20, 12), (64, 128, 2, 6, 10, 18), (128, 128, 1, 5, 17, 9),
-                                               (256, 256, 1, 4, 12, 12), (256, 128, 1, 6, 18, 10), (128, 64, 1, 8, 33, 17)])
+                                               (256, 256, 1, 4, 12, 12), (256, 128, 1, 6, 18, 10), (128, 64, 1, 8, 33, 17),
+                                               (128, 128, 1, 6, 22, 20), (128, 256, 2, 9, 35, 35),
+                                               (256, 128, 1, 7, 6, 9), (64, 128, 1, 5, 70, 12)])
 def test_conv3d_k3_tensor_core(cuda, lib, cin, cout, nb, d, h, w):
     """fp16 operands, fp32 accumulate: compare with F.conv3d on the SAME fp16-rounded operands in fp32."""
     from neuroclear_b200._lib import call, ptr, stream_ptr
@@ -297,7 +299,8 @@ def test_stats_finalize_shared_scratch_across_channel_counts(cuda, lib):
             assert torch.allclose(got[:, 0], mean, rtol=1e-6) and torch.allclose(got[:, 1], 1 / torch.sqrt(var + 1e-5), rtol=1e-5)
 
 
-@pytest.mark.parametrize("cin,cout,nb,d,h,w", [(64, 64, 2, 9, 20, 12), (128, 128, 1, 5, 17, 9), (256, 256, 1, 4, 12, 12)])
+@pytest.mark.parametrize("cin,cout,nb,d,h,w", [(64, 64, 2, 9, 20, 12), (128, 128, 1, 5, 17, 9), (256, 256, 1, 4, 12, 12),
+                                               (128, 128, 2, 7, 22, 19), (256, 256, 1, 9, 35, 35)])
 def test_conv3d_k3_fused_instance_norm_input(cuda, lib, cin, cout, nb, d, h, w):
     """in_mean_rstd != NULL: the kernel normalises + ReLUs the RAW input planes in shared memory.  Must equal the
     two-pass path (nc_in_relu_apply, then conv) BIT FOR BIT: same fp32 expression, same fp16 rounding."""
@@ -380,3 +383,38 @@ def test_conv3d_persistent_grid_cap_is_bit_identical(cuda, lib, cin, cout):
         lib.nc_debug_set_max_ctas(0)
     for y, st in outs[1:]:
         assert torch.equal(y, outs[0][0]) and torch.equal(st, outs[0][1])
+
+
+@pytest.mark.parametrize("cin,cout,nb,d,h,w,fused", [(128, 128, 2, 7, 22, 19, False), (256, 256, 1, 9, 35, 35, True),
+                                                     (64, 128, 1, 6, 70, 17, False), (128, 128, 1, 5, 5, 9, True)])
+def test_remainder_pair_kernel_is_bit_identical_to_the_regular_tiles(cuda, lib, cin, cout, nb, d, h, w, fused):
+    """H mod 16 in 1..6: the remainder strip of two consecutive planes shares one accumulator (conv3d_rp_kernel).
+    Same K order, same epilogue: the raw fp16 outputs must equal the regular kernel's (hook off) bit for bit; the
+    statistics are the same sums split over different tiles, so mean / rstd agree to fp32 rounding."""
+    from neuroclear_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = (torch.randn((nb, d, h, w, cin), generator=g) * 1.5 + 0.2).half().to(cuda)
+    mr_in = None
+    if fused:
+        mean = x.float().mean(dim=(1, 2, 3))
+        rstd = 1 / torch.sqrt(x.float().var(dim=(1, 2, 3), unbiased=False) + 1e-5)
+        mr_in = torch.stack([mean, rstd], 1).contiguous()
+    wt = (torch.randn((cout, cin, 3, 3, 3), generator=g) * (2.0 / (27 * cin)) ** 0.5).to(cuda)
+    packed = torch.empty(lib.nc_packed_weight_bytes(cout, cin, 0), dtype=torch.uint8, device=cuda)
+    call("nc_pack_weights_conv3d_k3", ptr(wt), cout, cin, ptr(packed), stream_ptr())
+    res = []
+    try:
+        for on in (1, 0):
+            lib.nc_debug_set_remainder_pairs(on)
+            rows = lib.nc_conv3d_k3_stats_rows(cin, nb, d, h, w, cout)
+            y = torch.full((nb, d, h, w, cout), float("nan"), dtype=torch.float16, device=cuda)
+            st = torch.full((rows * 2 * cout,), float("nan"), device=cuda)
+            call("nc_conv3d_k3_fwd", ptr(x), ptr(mr_in), nb, d, h, w, cin, ptr(packed), cout, ptr(y), ptr(st), stream_ptr())
+            mr = _finalize(lib, st, cin, nb, d, h, w, cout, cuda)
+            torch.cuda.synchronize()
+            res.append((y, mr.clone(), rows))
+    finally:
+        lib.nc_debug_set_remainder_pairs(1)
+    assert res[0][2] < res[1][2]                                   # fewer tiles with the remainder pairs
+    assert torch.isfinite(res[0][0].float()).all() and torch.equal(res[0][0], res[1][0])
+    assert torch.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-6)
