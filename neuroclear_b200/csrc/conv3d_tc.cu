@@ -90,7 +90,10 @@ struct ConvTcArgs {
   int total_tiles;
   int tiles_h_cap;   // > 0: the regular kernel covers only this many 16-line h-tiles (the rest is the RP kernel's)
   int rp_h0, rp_rem;  // remainder-pair kernel: first line and number of lines (1..6) of the remainder strip
-  int stats_tile0;    // remainder-pair kernel: first row of its tiles in stats_partial
+  // stats_partial rows are grouped per cube (in_stats_finalize reduces rows [nb * R, (nb + 1) * R)): with the
+  // remainder-pair kernel a cube's rows are [regular tiles | RP tiles]
+  int stats_nb_extra;  // regular kernel: RP tiles per cube (0 without RP): row = spatial + nb * stats_nb_extra
+  int stats_tile0;     // remainder-pair kernel: regular tiles per cube: row = spatial + (nb + 1) * stats_tile0
   const uint8_t* wpacked;
   // MODE 0
   __half* out_raw;       // [NB][D][H][W][ldo] raw conv output, fp16
@@ -602,7 +605,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         for (int i = e; args.stats_partial != nullptr && i < 2 * BN; i += 128) {
           const float s = (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
           const int which = i / BN, col = i - which * BN;
-          args.stats_partial[(static_cast<size_t>(t.spatial) * 2 + which) * args.ldo + t.n_tile * BN + col] = s;
+          args.stats_partial[(static_cast<size_t>(t.spatial + t.nb * args.stats_nb_extra) * 2 + which) * args.ldo +
+                             t.n_tile * BN + col] = s;
         }
         ptx::named_bar_sync(1, 128);
       }
@@ -933,7 +937,7 @@ conv3d_rp_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
       for (int i = e; args.stats_partial != nullptr && i < 2 * BN; i += 128) {
         const float s = (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
         const int which = i / BN, col = i - which * BN;
-        args.stats_partial[(static_cast<size_t>(args.stats_tile0 + t.spatial) * 2 + which) * args.ldo +
+        args.stats_partial[(static_cast<size_t>(t.spatial + (t.nb + 1) * args.stats_tile0) * 2 + which) * args.ldo +
                            t.n_tile * BN + col] = s;
       }
       ptx::named_bar_sync(1, 128);
@@ -1144,14 +1148,15 @@ int conv3d_k3_fwd(const void* x, const float* in_mean_rstd, int NB, int D, int H
   a.n_tiles = Cout / 128;
   if (const int rem = rp_rem(H, Cout)) {
     // full 16-line h-tiles by the regular kernel, the remainder strip (rem <= 6 lines) by the remainder-pair kernel
-    const int full = H / TH;
+    const int full = H / TH, tw = (W + TW - 1) / TW;
     if (full > 0) {
       a.tiles_h_cap = full;
+      a.stats_nb_extra = ((D + 3) / 4) * tw;
       if (int rc = launch_cfg<3, 128, 2, 0>(x, a, Cin, stream)) return rc;
     }
-    a.tiles_h_cap = 0;
+    a.tiles_h_cap = 0, a.stats_nb_extra = 0;
     a.rp_h0 = full * TH, a.rp_rem = rem;
-    a.stats_tile0 = NB * ((D + 1) / 2) * full * ((W + TW - 1) / TW);
+    a.stats_tile0 = ((D + 1) / 2) * full * tw;
     return launch_rp<128>(x, a, Cin, stream);
   }
   return launch_cfg<3, 128, 2, 0>(x, a, Cin, stream);
