@@ -467,6 +467,8 @@ def main():
     ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--config5", action="store_true", help="also measure the 1024x2048x2048 volume at N < 8")
+    ap.add_argument("--no-remainder-pairs", action="store_true",
+                    help="A/B measurement: disable the remainder-pair conv kernel (same results, more MMA rows)")
     args = ap.parse_args()
     shape = tuple(args.size)
 
@@ -479,6 +481,8 @@ def main():
     from neuroclear_b200 import networks
     from neuroclear_b200.unet_engine import FLOP_PER_VOXEL
 
+    if args.no_remainder_pairs:
+        _lib.load().nc_debug_set_remainder_pairs(0)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
