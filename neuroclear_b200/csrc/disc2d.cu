@@ -442,22 +442,58 @@ int lrelu_bwd(const float* dy, const float* y, long long n, float slope, float* 
 // ------------------------------------------------------------------------------------------------ losses
 // mode 0: MSE against a constant target (GANLoss lsgan, networks.py:275-276,311-313): mean((p - t)^2)
 // mode 1: L1 against a tensor (torch.nn.L1Loss, apollo_model.py:128,279):               mean(|p - q|)
+// One thread-block cluster (1 CTA for the small prediction maps, 8 CTAs for volumes): every thread strides over the
+// cluster's elements, block sums are tree-reduced in shared memory, and rank 0 adds the CTAs' sums through
+// distributed shared memory in rank order -> bitwise repeatable, no scratch buffer, one launch.  (A single 256-thread
+// block took ~0.4 ms for the L1 cycle term of a 108^3 crop: it sits in the critical path of every iteration.)
 __global__ void __launch_bounds__(256)
 loss_fwd_kernel(const float* __restrict__ p, const float* __restrict__ q, float target, long long n, int mode,
                 float* __restrict__ loss) {
   __shared__ double red[256];
+  __shared__ double block_sum;
+  const unsigned rank = cluster_rank_x(), csize = cluster_size_x();
   double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += 256) {
-    const float d = p[i] - (mode == 0 ? target : q[i]);
-    s += mode == 0 ? static_cast<double>(d) * d : fabs(static_cast<double>(d));
+  auto term = [&](float pv, float qv) {
+    const float d = pv - (mode == 0 ? target : qv);
+    return mode == 0 ? static_cast<double>(d) * d : fabs(static_cast<double>(d));
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q)) & 15) == 0;
+  const long long n4 = vec ? (n >> 2) : 0;
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+#pragma unroll 4
+  for (long long i = static_cast<long long>(rank) * 256 + threadIdx.x; i < n4; i += 256ll * csize) {
+    const float4 a = __ldg(p4 + i);
+    const float4 b = mode == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(q4 + i);
+    s += (term(a.x, b.x) + term(a.y, b.y)) + (term(a.z, b.z) + term(a.w, b.w));
   }
+  for (long long i = (n4 << 2) + static_cast<long long>(rank) * 256 + threadIdx.x; i < n; i += 256ll * csize)
+    s += term(p[i], mode == 0 ? 0.f : q[i]);
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o >= 1; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *loss = static_cast<float>(red[0] / static_cast<double>(n));
+  if (threadIdx.x == 0) block_sum = red[0];
+  if (csize == 1) {
+    if (threadIdx.x == 0) *loss = static_cast<float>(red[0] / static_cast<double>(n));
+    return;
+  }
+  cluster_sync_all();
+  if (rank == 0 && threadIdx.x == 0) {
+    double total = block_sum;
+    const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&block_sum));
+    for (unsigned r = 1; r < csize; ++r) {
+      unsigned remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      double v;
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote));
+      total += v;
+    }
+    *loss = static_cast<float>(total / static_cast<double>(n));
+  }
+  cluster_sync_all();  // remote shared memory must stay alive until rank 0 has read it
 }
 // dp = upstream * d loss / dp
 __global__ void loss_bwd_kernel(const float* __restrict__ p, const float* __restrict__ q, float target, long long n,
@@ -470,9 +506,9 @@ __global__ void loss_bwd_kernel(const float* __restrict__ p, const float* __rest
 }
 int loss_fwd(const float* p, const float* q, float target, long long n, int mode, float* loss, cudaStream_t stream) {
   if (mode != 0 && mode != 1) return set_error("loss: mode must be 0 (mse vs constant) or 1 (l1 vs tensor)");
-  loss_fwd_kernel<<<1, 256, 0, stream>>>(p, q, target, n, mode, loss);
-  NC_CUDA(cudaGetLastError());
-  return 0;
+  // with 8 CTAs of 256 threads a 108^3 volume is ~600 strided iterations per thread instead of ~4900
+  return launch_clustered(loss_fwd_kernel, dim3(n >= (1 << 16) ? 8 : 1), n >= (1 << 16) ? 8 : 1, stream, p, q, target,
+                          n, mode, loss);
 }
 int loss_bwd(const float* p, const float* q, float target, long long n, int mode, const float* upstream, float* dp,
              cudaStream_t stream) {

@@ -118,6 +118,45 @@ class _Loss(torch.autograd.Function):
         return dp, (-dp if (q is not None and ctx.needs_input_grad[1]) else None), None, None
 
 
+class _BatchedLsganLoss(torch.autograd.Function):
+    """Per-image LSGAN losses of a batched prediction map: out[i] = mean((pred[i] - target[i])^2), one nc_loss_fwd /
+    nc_loss_bwd per image on a slice of the batch (no torch slicing ops on the tape)."""
+
+    @staticmethod
+    def forward(ctx, pred, targets):
+        import ctypes as C
+        pred = _check(pred, "prediction")
+        n = pred.shape[0]
+        per = pred.numel() // n
+        out = torch.empty(n, dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            for i in range(n):
+                call("nc_loss_fwd", C.c_void_p(pred.data_ptr() + 4 * per * i), None, f32(targets[i]), i64(per), 0,
+                     C.c_void_p(out.data_ptr() + 4 * i), stream_ptr())
+        ctx.save_for_backward(pred)
+        ctx.targets = tuple(targets)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        pred, = ctx.saved_tensors
+        n = pred.shape[0]
+        per = pred.numel() // n
+        g = g.contiguous().float()
+        dp = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            for i in range(n):
+                call("nc_loss_bwd", C.c_void_p(pred.data_ptr() + 4 * per * i), None, f32(ctx.targets[i]), i64(per), 0,
+                     C.c_void_p(g.data_ptr() + 4 * i), C.c_void_p(dp.data_ptr() + 4 * per * i), stream_ptr())
+        return dp, None
+
+
+def batched_lsgan_losses(prediction, targets_are_real):
+    """GANLoss('lsgan') of every image of a batched prediction map -> float32 vector (N,)"""
+    return _BatchedLsganLoss.apply(prediction, tuple(1.0 if t else 0.0 for t in targets_are_real))
+
+
 class _PatchGANFn(torch.autograd.Function):
     """The whole discriminator in one call per direction (nc_patchgan_fwd / nc_patchgan_bwd): the 18 passes of a
     training iteration are launch-latency bound, so the layer loop lives inside the library, not in Python."""

@@ -45,10 +45,7 @@ def data_parallel_discriminator_step(rank, world, dev):
         sp.optimizer_D.zero_grad()
         np.random.seed(50 + r)
         real, fake, rec = crops(r)
-        sp.backward_D_A_lateral(real, fake)
-        sp.backward_D_A_axial(real, fake)
-        sp.backward_D_B_lateral(real, rec)
-        sp.backward_D_B_axial(real, rec)
+        sp.backward_D_all(real, fake, rec)
         for a, p in zip(acc, params):
             a += p.grad
     for a, p in zip(acc, params):

@@ -26,11 +26,13 @@ def _opt():
                      norm="instance", init_type="kaiming", init_gain=0.02, lr=1e-4, beta1=0.1, lambda_A=5.0)
 
 
-@pytest.fixture()
-def path(cuda):
+@pytest.fixture(params=[True, False], ids=["batched", "one-pass-per-slice"])
+def path(cuda, request):
+    """both forms of the discriminator passes (ApolloDiscriminatorPath.batched) against the same reference fixture"""
     from neuroclear_b200.apollo_d_path import ApolloDiscriminatorPath
     with redirect_stdout(io.StringIO()):
         p = ApolloDiscriminatorPath(_opt(), cuda)
+    p.batched = request.param
     for i, name in enumerate(D_NAMES):
         getattr(p, "net" + name).module.load_state_dict(odisc.random_state_dict(seed=10 + i))
     return p
