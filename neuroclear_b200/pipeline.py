@@ -22,6 +22,58 @@ from .dicing import (PercentileSelect, blend_gather, dice_extract, dice_geometry
 from .unet_engine import UnetDeconvEngine
 
 
+class ChunkedUpload:
+    """Input planes [z0, z0 + n) of a pinned host slab -> device slab, chunk by chunk on a copy stream.
+    ensure(z): every chunk containing planes below z has been produced by `source` (reader thread) and its H2D copy is
+    enqueued; wait_for(z): additionally makes the CURRENT stream wait for those copies."""
+
+    def __init__(self, slab_host, vol_dev, z0, copy_stream, chunks, source=None):
+        import queue
+        import threading
+        self.host, self.dev, self.z0, self.stream = slab_host, vol_dev, z0, copy_stream
+        n = slab_host.shape[0]
+        step = max(1, -(-n // chunks))
+        self.bounds = [(a, min(n, a + step)) for a in range(0, n, step)]
+        self.events = []             # one per enqueued chunk
+        self.waited = 0
+        self.error = None
+        self.filled = None
+        if source is not None:
+            self.filled = queue.Queue()
+
+            def reader():
+                try:
+                    for a, b in self.bounds:
+                        source(a, b)
+                        self.filled.put((a, b))
+                except BaseException as e:  # noqa: BLE001 - re-raised on the consumer side
+                    self.error = e
+                    self.filled.put(None)
+            self.thread = threading.Thread(target=reader, daemon=True)
+            self.thread.start()
+
+    def ensure(self, z_end):
+        while len(self.events) < len(self.bounds) and \
+                (not self.events or self.z0 + self.bounds[len(self.events) - 1][1] < z_end):
+            a, b = self.bounds[len(self.events)]
+            if self.filled is not None:
+                got = self.filled.get()
+                if got is None:
+                    raise self.error
+            with torch.cuda.stream(self.stream):
+                self.dev[a:b].copy_(self.host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self.events.append(ev)
+
+    def wait_for(self, z_end):
+        self.ensure(z_end)
+        cur = torch.cuda.current_stream()
+        while self.waited < len(self.events):
+            cur.wait_event(self.events[self.waited])
+            self.waited += 1
+
+
 class DicedInference:
     def __init__(self, state_dict, device, roi=120, overlap=15, border=10, normalize_intensity=True,
                  sat_level=(0.25, 99.75), batch=4, group=None, distributed=None):
@@ -76,27 +128,21 @@ class DicedInference:
         z0, z1 = plan["in_planes"]
         return volume_host[z0:z1].to(self.device, non_blocking=True), z0
 
-    def upload_chunked(self, slab_host: torch.Tensor, plan, chunks=16):
+    def upload_chunked(self, slab_host: torch.Tensor, plan, chunks=16, source=None):
         """H2D of this rank's input planes on a side stream, in z-chunks, so that the first cube batches start while
-        the rest of the slab is still crossing PCIe.  Returns (device slab, [(z_end, event)...]): infer_cubes makes
-        the compute stream wait for exactly the chunks a batch reads."""
+        the rest of the slab is still crossing PCIe.  Returns (device slab, ChunkedUpload): infer_cubes asks it for the
+        planes a batch reads.  `source` (optional) is a callable (a, b) -> None that FILLS slab_host[a:b] (e.g. reads
+        the planes from a file); it runs on a reader thread one chunk ahead, so disk, PCIe and compute overlap."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         z0, z1 = plan["in_planes"]
-        n = z1 - z0
         vol_dev = torch.empty(slab_host.shape, dtype=slab_host.dtype, device=self.device)
-        ready = []
-        step = max(1, -(-n // chunks))
         self._copy_stream.wait_stream(torch.cuda.current_stream())      # the allocation above is stream-ordered
-        with torch.cuda.stream(self._copy_stream):
-            for a in range(0, n, step):
-                b = min(n, a + step)
-                vol_dev[a:b].copy_(slab_host[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self._copy_stream)
-                ready.append((z0 + b, ev))
         vol_dev.record_stream(self._copy_stream)      # allocated on the compute stream, written on the copy stream
-        return vol_dev, ready
+        up = ChunkedUpload(slab_host, vol_dev, z0, self._copy_stream, chunks, source)
+        if source is None:
+            up.ensure(z1)                              # everything is already in host memory: enqueue all copies now
+        return vol_dev, up
 
     def infer_cubes(self, vol_dev, vol_z0, plan, queue=None, ready=None):
         self.out_dtype = vol_dev.dtype
@@ -107,14 +153,10 @@ class DicedInference:
             queue = torch.empty((c1 - c0, r, r, r), dtype=torch.float32, device=self.device)
         nbmax = min(self.batch, max(c1 - c0, 1))
         xbuf = torch.empty((nbmax, e, e, e), dtype=torch.float32, device=self.device)
-        waited = 0
         for b0 in range(c0, c1, nbmax):
             nb = min(nbmax, c1 - b0)
-            if ready:       # wait for the uploaded chunks this batch's cubes read (border and reflection included)
-                need = sharding.input_plane_range(geo, b0, b0 + nb)[1]
-                while waited < len(ready) and (waited == 0 or ready[waited - 1][0] < need):
-                    torch.cuda.current_stream().wait_event(ready[waited][1])
-                    waited += 1
+            if ready is not None:   # the uploaded chunks this batch's cubes read (border and reflection included)
+                ready.wait_for(sharding.input_plane_range(geo, b0, b0 + nb)[1])
             x = dice_extract(vol_dev, vol_z0, geo, b0, nb, out=xbuf[:nb])
             self.engine.forward(x, crop=self.border, out=queue[b0 - c0:b0 - c0 + nb], nb_cap=nbmax)
         return queue
@@ -159,26 +201,57 @@ class DicedInference:
             torch.cuda.current_stream().synchronize()
         return out_host.numpy(), plan["out_planes"]
 
-    def run_file(self, in_path, out_path):
+    def run_file(self, in_path, out_path, chunks=16):
         """test_dice.py end to end on files: read the (multi-page, uncompressed) TIFF volume `in_path`, run the path,
         write the result TIFF `out_path` (skimage.io.imread / tifffile.imsave in the reference, diceImage_dataset.py:35,
-        test_dice.py:151).  Sharded: every rank reads only the input planes it needs into pinned memory and writes
-        its own output slab into the shared file; rank 0 adds the header and the page directory."""
+        test_dice.py:151).  Streaming: a reader thread fills the pinned input slab chunk by chunk while earlier chunks
+        cross PCIe and the first cube batches already run; the result leaves in plane chunks whose D2H copies overlap
+        the file writes of the chunks before them.  Sharded: every rank reads only the input planes it needs and
+        writes its own output slab into the shared file; rank 0 adds the header and the page directory."""
         from . import volume_io
         tv = volume_io.TiffVolume(in_path)
         size = tv.shape
-        plan = self.plan(size)
-        z0, z1 = plan["in_planes"]
-        dt = torch.uint16 if tv.dtype.itemsize == 2 else torch.uint8
-        slab = torch.empty((z1 - z0,) + size[1:], dtype=dt).pin_memory()
-        tv.read(z0, z1, out=slab.numpy())
-        planes, (o0, o1) = self.run_slab(slab, z0, size)
-        layout = volume_io.TiffLayout(size, planes.dtype)
-        if self.rank == 0 and os.path.exists(out_path):
-            os.remove(out_path)
-        if self.world > 1:
-            dist.barrier(self.group)
-        volume_io.write_planes(out_path, layout, planes, o0, write_directory=self.rank == 0)
+        with torch.cuda.device(self.device):
+            plan = self.plan(size)
+            z0, z1 = plan["in_planes"]
+            dt = torch.uint16 if tv.dtype.itemsize == 2 else torch.uint8
+            slab = torch.empty((z1 - z0,) + size[1:], dtype=dt).pin_memory()
+            slab_np = slab.numpy()
+            vol_dev, ready = self.upload_chunked(
+                slab, plan, chunks, source=lambda a, b: tv.read(z0 + a, z0 + b, out=slab_np[a:b]))
+            out_dev = self.run_device(vol_dev, z0, size, ready=ready)
+            o0, o1 = plan["out_planes"]
+            layout = volume_io.TiffLayout(size, np.dtype("u2") if out_dev.dtype == torch.uint16 else np.dtype("u1"))
+            if self.rank == 0 and os.path.exists(out_path):
+                os.remove(out_path)
+            if self.world > 1:
+                dist.barrier(self.group)
+            # D2H in chunks through two pinned buffers; chunk k is written while chunk k + 1 is copied
+            n = o1 - o0
+            step = max(1, -(-n // chunks))
+            bufs = [torch.empty((step,) + size[1:], dtype=out_dev.dtype).pin_memory() for _ in range(2)]
+            evs = [None, None]
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
+            bounds = [(a, min(n, a + step)) for a in range(0, n, step)]
+
+            def issue(k):
+                a, b = bounds[k]
+                with torch.cuda.stream(self._copy_stream):
+                    bufs[k % 2][:b - a].copy_(out_dev[a:b], non_blocking=True)
+                    evs[k % 2] = torch.cuda.Event()
+                    evs[k % 2].record(self._copy_stream)
+            if bounds:
+                issue(0)
+            for k, (a, b) in enumerate(bounds):
+                evs[k % 2].synchronize()
+                if k + 1 < len(bounds):
+                    issue(k + 1)
+                volume_io.write_planes(out_path, layout, bufs[k % 2][:b - a].numpy(), o0 + a,
+                                       write_directory=(self.rank == 0 and k == 0))
+            if not bounds and self.rank == 0:
+                volume_io.write_planes(out_path, layout, np.empty((0,) + size[1:], dtype=layout.dtype), 0,
+                                       write_directory=True)
+            out_dev.record_stream(self._copy_stream)
         if self.world > 1:
             dist.barrier(self.group)
         return layout
