@@ -323,6 +323,29 @@ int nc_patchgan_bwd(const float* x, const float* dpred, int32_t n, int32_t h, in
                     const float* const* weights, float* ws, float* dx, float* const* dweights, float* const* dbiases,
                     nc_stream_t stream);
 
+/* ---- whole-network entry (nc_unet_deconv_infer_cube) ------------------------------------------------
+ * Unet_deconv.forward (models/networks.py:512-538) for nb cubes of d x h x w voxels (each divisible by 4) in ONE call:
+ * x float32 (nb, d, h, w) -> out float32 (nb, d-2c, h-2c, w-2c), sigmoid output with the border `crop` already cut
+ * (util/assemble_dice.py:143).  Weights are the PACKED images produced by the nc_pack_weights_* calls, in the order
+ * of the reference's state_dict (k3: double_conv1.3, double_conv2.0, double_conv2.3, bottom_layer.0/.3/.6,
+ * ex_double_conv2.0/.3, ex_conv1_1.0; ct: t_conv2, t_conv1; head = {one_by_one.weight[64], one_by_one.bias,
+ * one_by_one_2.weight, one_by_one_2.bias} float32).  workspace: nc_unet_deconv_workspace_bytes(...) bytes of device
+ * memory, initialised ONCE with nc_unet_deconv_workspace_init.  Stateless, asynchronous on `stream`, allocation-free:
+ * the call may be captured into a CUDA graph (fixed x / out / workspace) and replayed. */
+typedef struct nc_unet_deconv_weights {
+  const void* first;        /* nc_pack_weights_conv3d_cin1_k3 */
+  const void* k3[9];        /* nc_pack_weights_conv3d_k3 */
+  const void* ct[2];        /* nc_pack_weights_convT3d_k2s2 */
+  const float* ct_bias[2];  /* t_conv2.bias, t_conv1.bias */
+  const float* head;        /* 67 floats */
+} nc_unet_deconv_weights;
+int64_t nc_unet_deconv_workspace_bytes(int32_t nb, int32_t d, int32_t h, int32_t w);
+int nc_unet_deconv_workspace_init(void* workspace, int64_t workspace_bytes, int32_t nb, int32_t d, int32_t h, int32_t w,
+                                  nc_stream_t stream);
+int nc_unet_deconv_infer_cube(const float* x, int32_t nb, int32_t d, int32_t h, int32_t w,
+                              const nc_unet_deconv_weights* weights, void* workspace, int64_t workspace_bytes,
+                              int32_t crop, float* out, nc_stream_t stream);
+
 /* ---- remaining Assemble_Dice / test_dice.py options -------------------------------------------
  * --histogram_match (util/assemble_dice.py:150-151): skimage.exposure.match_histograms(fake, real) of one border-cut
  * cube (n = roi^3 float32 voxels each), skimage/exposure/histogram_matching.py::_match_cumulative_cdf restated:

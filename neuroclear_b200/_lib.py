@@ -81,6 +81,9 @@ SIGNATURES = {
     "nc_loss_fwd": (C.c_int, [vp, vp, f32, i64, i32, vp, vp]),
     "nc_loss_bwd": (C.c_int, [vp, vp, f32, i64, i32, vp, vp, vp]),
     "nc_adam_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
+    "nc_unet_deconv_workspace_bytes": (i64, [i32, i32, i32, i32]),
+    "nc_unet_deconv_workspace_init": (C.c_int, [vp, i64, i32, i32, i32, i32, vp]),
+    "nc_unet_deconv_infer_cube": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, i64, i32, vp, vp]),
     "nc_hist_match_scratch_bytes": (i64, [i64]),
     "nc_hist_match_f32": (C.c_int, [vp, vp, i64, vp, i64, vp, vp]),
     "nc_blend_gather_f64": (C.c_int, [vp, vp, vp, I3, I3, i32, i32, i32, i32, vp, vp]),

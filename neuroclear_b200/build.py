@@ -7,7 +7,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SOURCES = ["runtime.cu", "conv3d_tc.cu", "wgrad3d_tc.cu", "conv1_tc.cu", "elementwise.cu", "unet_bwd.cu", "deeplinear.cu", "disc2d.cu", "patchgan.cu", "augment.cu", "postprocess.cu", "api.cu"]
+SOURCES = ["runtime.cu", "conv3d_tc.cu", "wgrad3d_tc.cu", "conv1_tc.cu", "elementwise.cu", "unet_bwd.cu", "deeplinear.cu", "disc2d.cu", "patchgan.cu", "augment.cu", "postprocess.cu", "unet_infer.cu", "api.cu"]
 HEADERS = ["internal.h", "ptx.cuh", "augment_math.h"]
 OUT = os.path.join(_HERE, "libneuroclear_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

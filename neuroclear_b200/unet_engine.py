@@ -190,3 +190,48 @@ class UnetDeconvEngine:
 
     #: kernels launched by one forward(): 1 + 9 convs, 2 convT, 10 finalize, 5 apply(+pool), 1 head
     LAUNCHES_PER_FORWARD = 1 + 9 + 2 + 10 + 5 + 1
+
+    # ------------------------------------------------------------------ whole-network C entry
+    def _weights_struct(self):
+        """nc_unet_deconv_weights (include/neuroclear_b200.h): device pointers of the packed images"""
+        import ctypes as C
+
+        class W(C.Structure):
+            _fields_ = [("first", C.c_void_p), ("k3", C.c_void_p * 9), ("ct", C.c_void_p * 2),
+                        ("ct_bias", C.c_void_p * 2), ("head", C.c_void_p)]
+        w = W()
+        w.first = self.w_first.data_ptr()
+        for i, (prefix, _, _) in enumerate(_K3_LAYERS):
+            w.k3[i] = self.packed[prefix].data_ptr()
+        for i, (prefix, _, _) in enumerate(_CT_LAYERS):
+            w.ct[i] = self.packed[prefix].data_ptr()
+            w.ct_bias[i] = self.bias[prefix].data_ptr()
+        w.head = self.head.data_ptr()
+        return w
+
+    def forward_cube(self, x, crop: int = 0, out=None):
+        """forward() through ONE library call, nc_unet_deconv_infer_cube (the layer loop runs inside the library; same
+        kernels, same order, bit-identical results).  The call is allocation- and synchronisation-free, so it can be
+        captured in a CUDA graph (torch.cuda.graph) with fixed x / out tensors and replayed."""
+        import ctypes as C
+        if self.head is None:
+            raise _lib.NeuroclearError("UnetDeconvEngine: weights not loaded")
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4):
+            raise _lib.NeuroclearError("UnetDeconvEngine.forward_cube: x must be a contiguous float32 CUDA (NB,D,H,W) tensor")
+        nb, d, h, w = x.shape
+        lib = _lib.load()
+        need = lib.nc_unet_deconv_workspace_bytes(nb, d, h, w)
+        if need < 0:
+            raise _lib.NeuroclearError(lib.nc_last_error().decode())
+        if getattr(self, "_cube_ws_key", None) != (nb, d, h, w):
+            self._cube_ws = None
+            self._cube_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.nc_unet_deconv_workspace_init(ptr(self._cube_ws), i64(need), nb, d, h, w, stream_ptr()))
+            self._cube_ws_key = (nb, d, h, w)
+        if out is None:
+            out = torch.empty((nb, d - 2 * crop, h - 2 * crop, w - 2 * crop), dtype=torch.float32, device=x.device)
+        wts = self._weights_struct()
+        call("nc_unet_deconv_infer_cube", ptr(x), nb, d, h, w, C.byref(wts), ptr(self._cube_ws), i64(need), crop,
+             ptr(out), stream_ptr())
+        _lib.LAUNCHES += self.LAUNCHES_PER_FORWARD - 1       # `call` counted one
+        return out

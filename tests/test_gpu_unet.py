@@ -121,3 +121,32 @@ def test_rejects_bad_inputs(net, cuda):
             net(torch.zeros((1, 1, 18, 16, 16), device=cuda))     # not divisible by 4 (the reference's cat fails too)
         with pytest.raises(NeuroclearError):
             net.module(torch.zeros((1, 1, 16, 16, 16)))           # CPU tensor: no fallback
+
+
+def test_whole_cube_entry_is_bit_identical_and_graph_capturable(cuda):
+    """nc_unet_deconv_infer_cube: one library call for the whole network == the per-layer path bit for
+    bit; and, being allocation- and sync-free, it replays from a CUDA graph."""
+    from neuroclear_b200.unet_engine import UnetDeconvEngine
+    eng = UnetDeconvEngine(cuda)
+    eng.load_state_dict(ounet.random_state_dict(seed=0, bias_std=0.1))
+    x = torch.rand((2, 24, 40, 32), generator=torch.Generator().manual_seed(3)).to(cuda)
+    want = eng.forward(x, crop=4).clone()
+    got = eng.forward_cube(x, crop=4)
+    assert got.shape == (2, 16, 32, 24) and torch.equal(got, want)
+    # CUDA graph: capture once, replay on new input written into the same buffer
+    xs = x.clone()
+    ys = torch.empty_like(got)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eng.forward_cube(xs, crop=4, out=ys)                 # warm-up on the capture stream (workspace, attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.forward_cube(xs, crop=4, out=ys)
+    x2 = torch.rand((2, 24, 40, 32), generator=torch.Generator().manual_seed(4)).to(cuda)
+    xs.copy_(x2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(ys, eng.forward(x2, crop=4))
