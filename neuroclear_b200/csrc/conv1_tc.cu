@@ -141,65 +141,79 @@ conv_cin1_tc_kernel(const __grid_constant__ CUtensorMap tmapOut, const Conv1Args
         pre[e] = in ? __ldg(xin + (static_cast<size_t>(gz) * args.H + gy) * args.W + gx) : 0.f;
       }
     };
-    float pre[NPRE];
-    int nb = 0, tile = blockIdx.x;
-    bool have = tile < args.tiles_per_cube && args.NB > 0;
-    if (have) fetch(nb, tile, pre);
-    for (int it = 0; have; ++it) {
+    // software pipeline: the halos of the NEXT THREE tiles are in flight in registers while the current tile is
+    // converted — one tile of look-ahead left the loop waiting ~one L2 / DRAM latency per tile (2.2 TB/s of output)
+    constexpr int PF = 3;
+    float pre[PF][NPRE];
+    int fnb = 0, ftile = blockIdx.x;                       // fetch cursor
+    bool fhave = ftile < args.tiles_per_cube && args.NB > 0;
+    auto fetch_next = [&](float (&dst)[NPRE]) {
+      if (!fhave) return;
+      fetch(fnb, ftile, dst);
+      ftile += gridDim.x;
+      if (ftile >= args.tiles_per_cube) {
+        ftile = blockIdx.x;
+        ++fnb;
+      }
+      fhave = fnb < args.NB;
+    };
+    const int per_cube = fhave ? (args.tiles_per_cube - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                     static_cast<int>(gridDim.x)
+                               : 0;
+    const int total = per_cube * args.NB;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) fetch_next(pre[u]);
+    auto step = [&](int it, float (&cur)[NPRE]) {
       const int st = it & (NA - 1);
       ptx::mbar_wait(&aEmpty[st], ((it / NA) & 1) ^ 1);
       uint32_t* hl = reinterpret_cast<uint32_t*>(halo) + st * HALO_PITCH;
 #pragma unroll
       for (int e = 0; e < NPRE; ++e)
         if (pt + 128 * e < HALO_FLOATS) {
-          const __half h = __float2half_rn(pre[e]);
-          hl[pt + 128 * e] = pack_h2(h, __float2half_rn(pre[e] - __half2float(h)));   // (hi, lo)
+          const __half h = __float2half_rn(cur[e]);
+          hl[pt + 128 * e] = pack_h2(h, __float2half_rn(cur[e] - __half2float(h)));   // (hi, lo)
         }
-      // advance to the next tile of this CTA (tiles of cube nb, then cube nb+1, ...) and start its loads
-      tile += gridDim.x;
-      if (tile >= args.tiles_per_cube) {
-        tile = blockIdx.x;
-        ++nb;
-      }
-      have = nb < args.NB;
-      if (have) fetch(nb, tile, pre);
-      {
-        ptx::named_bar_sync(3, 128);
-        uint32_t kw32[32];  // the voxel's K-row: word t = (hi, lo) of tap t, words 27..31 zero
+      fetch_next(cur);                                     // the registers are free again: start tile it + PF
+      ptx::named_bar_sync(3, 128);
+      uint32_t kw32[32];  // the voxel's K-row: word t = (hi, lo) of tap t, words 27..31 zero
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd)
+      for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) kw32[(kd * 3 + kh) * 3 + kw] = hl[(kd * HH + mh + kh) * HW + mw + kw];
+          for (int kw = 0; kw < 3; ++kw) kw32[(kd * 3 + kh) * 3 + kw] = hl[(kd * HH + mh + kh) * HW + mw + kw];
 #pragma unroll
-        for (int t = 27; t < 32; ++t) kw32[t] = 0u;
-        uint8_t* row = smA + st * A_BYTES + pt * 128;
+      for (int t = 27; t < 32; ++t) kw32[t] = 0u;
+      uint8_t* row = smA + st * A_BYTES + pt * 128;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<uint4*>(row + ((u ^ (pt & 7)) << 4)) =
-              make_uint4(kw32[4 * u], kw32[4 * u + 1], kw32[4 * u + 2], kw32[4 * u + 3]);
-        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
-        ptx::named_bar_sync(3, 128);  // the whole stage is written and fenced
-        if (warp == 4) {
-          // producer warp 4 doubles as the MMA issuer (8 warps keep the register cap at 255: the epilogue holds
-          // 128 running statistics per thread)
-          const int slot = it & (NACC - 1);
-          if (it == 0) ptx::mbar_wait(bFull, 0);
-          ptx::mbar_wait(&accEmpty[slot], ((it / NACC) & 1) ^ 1);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t a_lo = (((smA_u32 + st * A_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(row + ((u ^ (pt & 7)) << 4)) =
+            make_uint4(kw32[4 * u], kw32[4 * u + 1], kw32[4 * u + 2], kw32[4 * u + 3]);
+      ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+      ptx::named_bar_sync(3, 128);  // the whole stage is written and fenced
+      if (warp == 4) {
+        // producer warp 4 doubles as the MMA issuer (8 warps keep the register cap at 255: the epilogue holds
+        // 128 running statistics per thread)
+        const int slot = it & (NACC - 1);
+        if (it == 0) ptx::mbar_wait(bFull, 0);
+        ptx::mbar_wait(&accEmpty[slot], ((it / NACC) & 1) ^ 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_lo = (((smA_u32 + st * A_BYTES) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(tmem_base + slot * 64, (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2 * k),
-                            (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + 2 * k), idesc, k == 0 ? 0u : 1u);
-            ptx::umma_commit(&aEmpty[st]);
-            ptx::umma_commit(&accFull[slot]);
-          }
-          __syncwarp();
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_f16(tmem_base + slot * 64, (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2 * k),
+                          (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + 2 * k), idesc, k == 0 ? 0u : 1u);
+          ptx::umma_commit(&aEmpty[st]);
+          ptx::umma_commit(&accFull[slot]);
         }
+        __syncwarp();
       }
+    };
+    for (int it = 0; it < total; it += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u)
+        if (it + u < total) step(it + u, pre[u]);
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ epilogue
