@@ -90,6 +90,24 @@ class FusedAdam(torch.optim.Optimizer):
                     torch.autograd.graph.increment_version(p)
 
 
+class _params_require_grad:
+    """requires_grad_(True) on the discriminators' parameters for the duration of the block, restoring the previous
+    flags afterwards (the tape of a pending generator backward recorded them as frozen)."""
+
+    def __init__(self, nets):
+        self.params = [p for n in nets for p in n.parameters()]
+
+    def __enter__(self):
+        self.prev = [p.requires_grad for p in self.params]
+        for p in self.params:
+            p.requires_grad_(True)
+
+    def __exit__(self, *a):
+        for p, f in zip(self.params, self.prev):
+            p.requires_grad_(f)
+        return False
+
+
 class _nullcontext:
     def __enter__(self):
         return self
@@ -261,7 +279,25 @@ class ApolloDiscriminatorPath:
                 self.backward_D_B_lateral(real, rec)
                 self.backward_D_B_axial(real, rec)
 
-    # ---- discriminator half of optimize_parameters (:297-307)
+    # ---- discriminator half of optimize_parameters (:297-307), in two parts so that the gradient computation can be
+    # enqueued on a side stream while the generators' backward runs (apollo_model.overlap_d_step)
+    def d_gradients(self, real, fake, rec):
+        # NOTE: requires_grad of the D parameters is NOT touched here — the generators' backward (which needs them
+        # frozen) may still be pending on the tape; _PatchGANFn computes parameter gradients on request
+        self.optimizer_D.zero_grad()
+        with _params_require_grad(self.discriminators()):
+            self.backward_D_all(real, fake, rec)
+
+    def d_update(self):
+        if self.device.type == "cuda":      # the gradients were produced on a side stream and are consumed on this one
+            cur = torch.cuda.current_stream(self.device)
+            for p in self.optimizer_D.params:
+                if p.grad is not None:
+                    p.grad.record_stream(cur)
+        if self.distributed:    # one crop per GPU; gradients averaged over the ranks before the update
+            allreduce_mean_gradients(self.optimizer_D.params, self.group)
+        self.optimizer_D.step()
+
     def optimize_D(self, real, fake, rec):
         for net in self.discriminators():
             for p in net.parameters():

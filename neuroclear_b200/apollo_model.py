@@ -137,15 +137,41 @@ class AxialToLateralGANApolloModel:
         self.loss_G = self.dpath.generator_losses(self.real, self.fake, self.rec)
         self.loss_G.backward()
 
+    #: True: the discriminators' forward / backward of the D update (small, latency-bound kernels) are enqueued on a
+    #: side stream BEFORE the generators' backward and run in its shadow; the two Adam steps keep the reference's
+    #: order.  Legal because the D gradients depend only on real / fake / rec and the CURRENT D weights (the G update
+    #: does not touch them), and backward_G only READS the D weights.  np.random draws keep the reference's order
+    #: (generator-side draws first, then the D-side draws).  False: strictly sequential, as written in the reference.
+    overlap_d_step = True
+
     # ---- :285-307
     def optimize_parameters(self):
         self.forward()
         self.optimizer_G.zero_grad()
-        self.backward_G()                       # the Ds are frozen inside generator_losses (set_requires_grad False)
+        if not self.overlap_d_step:
+            self.backward_G()                   # the Ds are frozen inside generator_losses (set_requires_grad False)
+            if self.distributed:
+                allreduce_mean_gradients(self.optimizer_G.params, self.group)
+            self.optimizer_G.step()
+            self.dpath.optimize_D(self.real, self.fake.detach(), self.rec.detach())
+            return
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_d_stream", None) is None:
+            self._d_stream = torch.cuda.Stream(self.device)
+        side = self._d_stream
+        self.loss_G = self.dpath.generator_losses(self.real, self.fake, self.rec)     # draws + D forwards (frozen Ds)
+        fake, rec = self.fake.detach(), self.rec.detach()
+        side.wait_stream(main)                  # fake / rec / the generator-side D passes are enqueued before this
+        with torch.cuda.stream(side):
+            for t in (self.real, fake, rec):
+                t.record_stream(side)
+            self.dpath.d_gradients(self.real, fake, rec)      # zero_grad + the six D losses' backward, no update yet
+        self.loss_G.backward()                  # on the main stream, concurrently with the side stream
         if self.distributed:
             allreduce_mean_gradients(self.optimizer_G.params, self.group)
         self.optimizer_G.step()
-        self.dpath.optimize_D(self.real, self.fake.detach(), self.rec.detach())
+        main.wait_stream(side)
+        self.dpath.d_update()
 
     def get_current_losses(self):
         out = OrderedDict()
