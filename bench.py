@@ -467,6 +467,8 @@ def main():
     ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--config5", action="store_true", help="also measure the 1024x2048x2048 volume at N < 8")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="experimental: cube batches alternate between this many CUDA streams (1 = serial batches)")
     ap.add_argument("--no-remainder-pairs", action="store_true",
                     help="A/B measurement: disable the remainder-pair conv kernel (same results, more MMA rows)")
     args = ap.parse_args()
@@ -510,7 +512,8 @@ def main():
 
     def measure(shape, steps, warmup, with_roofline):
         """One volume shape: device-resident timing, e2e timing, the digest of the e2e output."""
-        pipe = DicedInference(sd, dev, ROI, OVERLAP, BORDER, normalize_intensity=True, batch=args.batch)
+        pipe = DicedInference(sd, dev, ROI, OVERLAP, BORDER, normalize_intensity=True, batch=args.batch,
+                              streams=args.streams)
         plan = pipe.plan(shape)
         geo = plan["geo"]
         z0, z1 = plan["in_planes"]
@@ -525,7 +528,8 @@ def main():
             sampler = ClockSampler(local)
             sampler.start()
             launches0 = _lib.LAUNCHES
-            pipe.engine.profile = [] if profile else None
+            for eng in pipe.engines:
+                eng.profile = [] if profile else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             e0.record()
@@ -535,7 +539,9 @@ def main():
             barrier()
             ms = e0.elapsed_time(e1)
             clocks = sampler.stop()
-            prof, pipe.engine.profile = pipe.engine.profile, None
+            prof = [p for eng in pipe.engines for p in (eng.profile or [])] if profile else None
+            for eng in pipe.engines:
+                eng.profile = None
             if world > 1:
                 t = torch.tensor([ms], device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -624,7 +630,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "fp16", "data": "synthetic",
-            "config": workload_config(shape, world), "batch_cubes": args.batch,
+            "config": workload_config(shape, world), "batch_cubes": args.batch, "streams": args.streams,
             "clocks": main_res["clocks"],
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["launches"],

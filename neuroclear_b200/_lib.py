@@ -116,6 +116,8 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.nc_abi_version() != 1:
             raise NeuroclearError("libneuroclear_b200.so ABI version mismatch; rebuild")
+        if os.environ.get("NEUROCLEAR_REMAINDER_PAIRS", "1") == "0":      # A/B and debugging hook
+            lib.nc_debug_set_remainder_pairs(0)
         _lib = lib
     return _lib
 

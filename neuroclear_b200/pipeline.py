@@ -35,7 +35,7 @@ class ChunkedUpload:
         step = max(1, -(-n // chunks))
         self.bounds = [(a, min(n, a + step)) for a in range(0, n, step)]
         self.events = []             # one per enqueued chunk
-        self.waited = 0
+        self.waited = {}             # stream handle -> number of chunk events that stream already waits for
         self.error = None
         self.filled = None
         if source is not None:
@@ -67,16 +67,19 @@ class ChunkedUpload:
             self.events.append(ev)
 
     def wait_for(self, z_end):
+        """the CURRENT stream waits for every chunk enqueued so far (each stream keeps its own cursor)"""
         self.ensure(z_end)
         cur = torch.cuda.current_stream()
-        while self.waited < len(self.events):
-            cur.wait_event(self.events[self.waited])
-            self.waited += 1
+        done = self.waited.get(cur.cuda_stream, 0)
+        while done < len(self.events):
+            cur.wait_event(self.events[done])
+            done += 1
+        self.waited[cur.cuda_stream] = done
 
 
 class DicedInference:
     def __init__(self, state_dict, device, roi=120, overlap=15, border=10, normalize_intensity=True,
-                 sat_level=(0.25, 99.75), batch=4, group=None, distributed=None):
+                 sat_level=(0.25, 99.75), batch=4, group=None, distributed=None, streams=1):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise NeuroclearError("DicedInference needs a CUDA device (no CPU fallback)")
@@ -89,9 +92,20 @@ class DicedInference:
         self.distributed = dist.is_initialized() if distributed is None else distributed
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
+        #: EXPERIMENTAL (default 1 = strictly serial batches).  With streams = 2 cube batches alternate between two
+        #: CUDA streams, each with its own engine workspace: while one batch sits in a tensor-bound convolution the
+        #: other batch's memory-bound kernels (InstanceNorm apply / pool, head, dice — a quarter of a batch's time)
+        #: run in its shadow.  Values are unchanged (batches are independent; same out_sha256), but on a power-capped
+        #: B200 the gain is only 1 % (3025 -> 2994 ms on one box: the overlap raises the average power and the clock
+        #: drops 1590 -> 1540 MHz), per-launch CUDA-event times stop being kernel times, and a run with three streams
+        #: died with an unspecified launch failure that was not tracked down — so it is off by default.
+        self.n_streams = max(1, int(streams))
         with torch.cuda.device(self.device):
-            self.engine = UnetDeconvEngine(self.device)
-            self.engine.load_state_dict(state_dict)
+            self.engines = [UnetDeconvEngine(self.device) for _ in range(self.n_streams)]
+            for e in self.engines:
+                e.load_state_dict(state_dict)
+            self.engine = self.engines[0]
+            self._streams = None
             self.select = PercentileSelect(self.device)
         self._plan_key = None
         self._copy_stream = None
@@ -152,13 +166,29 @@ class DicedInference:
         if queue is None:
             queue = torch.empty((c1 - c0, r, r, r), dtype=torch.float32, device=self.device)
         nbmax = min(self.batch, max(c1 - c0, 1))
-        xbuf = torch.empty((nbmax, e, e, e), dtype=torch.float32, device=self.device)
-        for b0 in range(c0, c1, nbmax):
+        n_batches = -(-(c1 - c0) // nbmax)
+        ns = min(self.n_streams, max(n_batches, 1))
+        xbufs = [torch.empty((nbmax, e, e, e), dtype=torch.float32, device=self.device) for _ in range(ns)]
+        main = torch.cuda.current_stream()
+        if ns > 1:
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream(self.device) for _ in range(self.n_streams)]
+            lanes = self._streams[:ns]
+            for st in lanes:
+                st.wait_stream(main)              # vol_dev / queue / xbufs were allocated (and uploaded) on `main`
+        else:
+            lanes = [main]
+        for bi, b0 in enumerate(range(c0, c1, nbmax)):
             nb = min(nbmax, c1 - b0)
-            if ready is not None:   # the uploaded chunks this batch's cubes read (border and reflection included)
-                ready.wait_for(sharding.input_plane_range(geo, b0, b0 + nb)[1])
-            x = dice_extract(vol_dev, vol_z0, geo, b0, nb, out=xbuf[:nb])
-            self.engine.forward(x, crop=self.border, out=queue[b0 - c0:b0 - c0 + nb], nb_cap=nbmax)
+            k = bi % ns
+            with torch.cuda.stream(lanes[k]):
+                if ready is not None:   # the uploaded chunks this batch's cubes read (border and reflection included)
+                    ready.wait_for(sharding.input_plane_range(geo, b0, b0 + nb)[1])
+                x = dice_extract(vol_dev, vol_z0, geo, b0, nb, out=xbufs[k][:nb])
+                self.engines[k].forward(x, crop=self.border, out=queue[b0 - c0:b0 - c0 + nb], nb_cap=nbmax)
+        if ns > 1:
+            for st in lanes:
+                main.wait_stream(st)
         return queue
 
     def assemble(self, queue, plan):
