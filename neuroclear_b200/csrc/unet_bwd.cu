@@ -292,69 +292,108 @@ head_bwd_kernel(const __half* __restrict__ raw, const float* __restrict__ mr, co
 }
 
 // ------------------------------------------------------------------------------------------------ first layer wgrad
-// dW[co][tap] = sum_v dy[v][co] * x[v + tap - 1] for the Cin = 1 k3 conv (networks.py:420).  Thread = 4 output
-// channels x 27 taps in registers; 16 voxel lanes per block are combined in lane order.
+// dW[co][tap] = sum_v dy[v][co] * x[v + tap - 1] for the Cin = 1 k3 conv (networks.py:420; also dK of the folded
+// DeepLinear tail).  2.2 GMAC per 108^3 crop on the CUDA cores: the job is to keep the FMA pipe fed.
+// A block owns tiles of 4 x 8 x 16 voxels: the fp32 halo of x (6 x 10 x 18) and the 16-bit dy tile (64 KB) are staged
+// in shared memory; thread = (8 output channels) x (the 9 in-plane taps of ONE kd) x (one of 8 voxel lanes): per voxel
+// one 16-byte dy load + 9 broadcast x loads feed 72 FMAs (the round-1 kernel issued 27 L1 loads per 108 FMAs from
+// every one of the 16 threads that shared a voxel and ran at 155 clk per voxel per SM; the FMA bound is 13.5).
+// Voxel lanes are combined in lane order, blocks in block order (colsum_finalize_kernel): bitwise repeatable.
+namespace w1 {
+constexpr int TZ = 4, TY = 8, TX = 16, VOX = TZ * TY * TX;
+constexpr int HZ = TZ + 2, HY = TY + 2, HX = TX + 2, HALO = HZ * HY * HX;
+constexpr int THREADS = 192;  // 8 channel groups x 8 voxel lanes x 3 kd
+constexpr int SMEM_BYTES = VOX * 8 * 16 + HALO * 4;
+}  // namespace w1
+
 template <bool F16>
-__global__ void __launch_bounds__(256)
-conv1_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dy, int D, int H, int W,
-                   float* __restrict__ partial) {
-  __shared__ float acc_s[27 * 64];
+__global__ void __launch_bounds__(w1::THREADS)
+conv1_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dy, int D, int H, int W, int tiles_y,
+                   int tiles_x, int tiles, float* __restrict__ partial) {
+  using namespace w1;
+  extern __shared__ __align__(16) uint8_t w1_smem[];
+  uint4* dys = reinterpret_cast<uint4*>(w1_smem);                      // [VOX][8]: 64 channels of one voxel
+  float* xs = reinterpret_cast<float*>(w1_smem + VOX * 8 * 16);         // [HZ][HY][HX]
   const int nb = blockIdx.y;
-  const int g = threadIdx.x & 15, lane = threadIdx.x >> 4;
-  float acc[27][4];
+  const int cg = threadIdx.x & 7, vl = (threadIdx.x >> 3) & 7, kd = threadIdx.x >> 6;
+  float acc[9][8];
 #pragma unroll
-  for (int t = 0; t < 27; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-  const unsigned voxels = static_cast<unsigned>(D) * H * W;
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  const size_t voxels = static_cast<size_t>(D) * H * W;
   const float* xc = x + static_cast<size_t>(nb) * voxels;
-  for (unsigned v = blockIdx.x * 16u + lane; v < voxels; v += gridDim.x * 16u) {
-    const int w = v % W;
-    const unsigned r = v / W;
-    const int h = r % H, d = r / H;
-    const uint2 rawg = __ldg(reinterpret_cast<const uint2*>(dy + (static_cast<size_t>(nb) * voxels + v) * 64 + g * 4));
-    float2 ga, gb;
-    if constexpr (F16) {
-      const __half2* g2 = reinterpret_cast<const __half2*>(&rawg);
-      ga = __half22float2(g2[0]), gb = __half22float2(g2[1]);
-    } else {
-      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&rawg);
-      ga = __bfloat1622float2(g2[0]), gb = __bfloat1622float2(g2[1]);
+  const uint16_t* dyc = dy + static_cast<size_t>(nb) * voxels * 64;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int r = tile / tiles_x;
+    const int ty = r % tiles_y, tz = r / tiles_y;
+    const int z0 = tz * TZ, y0 = ty * TY, x0 = tx * TX;
+    __syncthreads();  // the previous tile has been consumed
+    for (int i = threadIdx.x; i < HALO; i += THREADS) {
+      const int hx = i % HX, hy = (i / HX) % HY, hz = i / (HX * HY);
+      const int gz = z0 + hz - 1, gy = y0 + hy - 1, gx = x0 + hx - 1;
+      const bool in = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      xs[i] = in ? __ldg(xc + (static_cast<size_t>(gz) * H + gy) * W + gx) : 0.f;
     }
-#pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-      const int zd = d + kd - 1;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int zh = h + kh - 1;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int zw = w + kw - 1;
-          const bool in = zd >= 0 && zd < D && zh >= 0 && zh < H && zw >= 0 && zw < W;
-          const float xv = in ? __ldg(xc + (static_cast<size_t>(zd) * H + zh) * W + zw) : 0.f;
-          const int t = (kd * 3 + kh) * 3 + kw;
-          acc[t][0] = fmaf(ga.x, xv, acc[t][0]);
-          acc[t][1] = fmaf(ga.y, xv, acc[t][1]);
-          acc[t][2] = fmaf(gb.x, xv, acc[t][2]);
-          acc[t][3] = fmaf(gb.y, xv, acc[t][3]);
-        }
-      }
+    for (int i = threadIdx.x; i < VOX * 8; i += THREADS) {
+      const int v = i >> 3, part = i & 7;
+      const int lx = v % TX, ly = (v / TX) % TY, lz = v / (TX * TY);
+      const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+      uint4 g = make_uint4(0u, 0u, 0u, 0u);  // voxels outside the volume contribute nothing
+      if (gz < D && gy < H && gx < W)
+        g = __ldg(reinterpret_cast<const uint4*>(dyc + ((static_cast<size_t>(gz) * H + gy) * W + gx) * 64) + part);
+      dys[i] = g;
     }
-  }
-  for (int l = 0; l < 16; ++l) {
-    if (lane == l) {
-#pragma unroll
-      for (int t = 0; t < 27; ++t)
+    __syncthreads();
+#pragma unroll 2
+    for (int v = vl; v < VOX; v += 8) {
+      const int lx = v % TX, ly = (v / TX) % TY, lz = v / (TX * TY);
+      const uint4 raw = dys[v * 8 + cg];
+      float gf[8];
+      if constexpr (F16) {
+        const __half2* g2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int idx = (g * 4 + i) * 27 + t;  // [co][tap], the weight's own layout
-          acc_s[idx] = (l == 0 ? 0.f : acc_s[idx]) + acc[t][i];
+          const float2 f = __half22float2(g2[i]);
+          gf[2 * i] = f.x, gf[2 * i + 1] = f.y;
+        }
+      } else {
+        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(g2[i]);
+          gf[2 * i] = f.x, gf[2 * i + 1] = f.y;
+        }
+      }
+      const float* xb = xs + ((lz + kd) * HY + ly) * HX + lx;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float xv = xb[kh * HX + kw];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(gf[i], xv, acc[kh * 3 + kw][i]);
+        }
+    }
+  }
+  // voxel lanes -> block, in lane order; red[co][tap] is the weight's own layout
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(w1_smem);
+  for (int l = 0; l < 8; ++l) {
+    if (vl == l) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = (cg * 8 + i) * 27 + kd * 9 + t;
+          red[idx] = (l == 0 ? 0.f : red[idx]) + acc[t][i];
         }
     }
     __syncthreads();
   }
   float* dst = partial + (static_cast<size_t>(nb) * gridDim.x + blockIdx.x) * (27 * 64);
-  for (int i = threadIdx.x; i < 27 * 64; i += 256) dst[i] = acc_s[i];
+  for (int i = threadIdx.x; i < 27 * 64; i += THREADS) dst[i] = red[i];
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -494,12 +533,21 @@ int conv1_wgrad(const float* x, const void* dy, int dy_fmt, int NB, int D, int H
                 cudaStream_t stream) {
   if (static_cast<long long>(D) * H * W >= (1ll << 31)) return set_error("conv1_wgrad: cube too large");
   const int blocks = bwd_blocks() / 4;
-  if (dy_fmt)
-    conv1_wgrad_kernel<false><<<dim3(blocks, NB), 256, 0, stream>>>(x, static_cast<const uint16_t*>(dy), D, H, W,
-                                                                    scratch);
-  else
-    conv1_wgrad_kernel<true><<<dim3(blocks, NB), 256, 0, stream>>>(x, static_cast<const uint16_t*>(dy), D, H, W,
-                                                                   scratch);
+  const int tz = (D + w1::TZ - 1) / w1::TZ, ty = (H + w1::TY - 1) / w1::TY, tx = (W + w1::TX - 1) / w1::TX;
+  static bool attr[2][64] = {{false}};
+  if (dy_fmt) {
+    if (first_use_on_device(attr[1]))
+      NC_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   w1::SMEM_BYTES));
+    conv1_wgrad_kernel<false><<<dim3(blocks, NB), w1::THREADS, w1::SMEM_BYTES, stream>>>(
+        x, static_cast<const uint16_t*>(dy), D, H, W, ty, tx, tz * ty * tx, scratch);
+  } else {
+    if (first_use_on_device(attr[0]))
+      NC_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   w1::SMEM_BYTES));
+    conv1_wgrad_kernel<true><<<dim3(blocks, NB), w1::THREADS, w1::SMEM_BYTES, stream>>>(
+        x, static_cast<const uint16_t*>(dy), D, H, W, ty, tx, tz * ty * tx, scratch);
+  }
   NC_CUDA(cudaGetLastError());
   colsum_finalize_kernel<<<dim3(1728 / 32, 1), 256, 0, stream>>>(scratch, blocks * NB, 1728, 1.0, dw);
   NC_CUDA(cudaGetLastError());
