@@ -297,28 +297,47 @@ def time_apollo_iterations(dev, crop, iters, warmup, distributed, rank=0, barrie
         model = AxialToLateralGANApolloModel(apollo_opt(dev.index or 0), dev, distributed=distributed)
     g = torch.Generator().manual_seed(100 + rank)      # a different crop per rank
     crops = [torch.rand((1, 1, crop, crop, crop), generator=g).pin_memory() for _ in range(2)]
-    times, launches, ar = [], 0, []
-    for i in range(warmup + iters):
+    # Steady-state throughput, as the reference's training loop runs it (train_onecube.py:83-110 never synchronises
+    # between iterations): W warm-up iterations, then K iterations enqueued back to back between two CUDA events, ONE
+    # synchronisation at the end.  (Synchronising after every iteration adds the ~2 ms the host needs to enqueue the
+    # next forward to each iteration: that latency figure is returned as well.)
+    launches, ar = 0, []
+    for i in range(warmup):
         if barrier is not None:
             barrier()
-        apollo_d_path.ALLREDUCE_EVENTS = [] if distributed else None
+        model.set_input({"A": crops[i % 2], "A_paths": "synthetic"})
+        model.optimize_parameters()
+    torch.cuda.synchronize()
+    lat = []
+    for i in range(3):                                      # per-iteration latency (synchronised every iteration)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = _lib.LAUNCHES
         e0.record()
         model.set_input({"A": crops[i % 2], "A_paths": "synthetic"})
         model.optimize_parameters()
         e1.record()
         torch.cuda.synchronize()
-        launches = _lib.LAUNCHES - n0
-        if i >= warmup:
-            times.append(e0.elapsed_time(e1))
-            if distributed:
-                ar.append(sum(a.elapsed_time(b) for a, b in apollo_d_path.ALLREDUCE_EVENTS))
+        lat.append(e0.elapsed_time(e1))
+    time_apollo_iterations.last_latency_ms = sum(lat) / len(lat)
+    if barrier is not None:
+        barrier()
+    apollo_d_path.ALLREDUCE_EVENTS = [] if distributed else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = _lib.LAUNCHES
+    e0.record()
+    for i in range(iters):
+        model.set_input({"A": crops[i % 2], "A_paths": "synthetic"})
+        model.optimize_parameters()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = (_lib.LAUNCHES - n0) // iters
+    times = [e0.elapsed_time(e1) / iters]
+    if distributed:
+        ar = [sum(a.elapsed_time(b) for a, b in apollo_d_path.ALLREDUCE_EVENTS) / iters]
     apollo_d_path.ALLREDUCE_EVENTS = None
     return sum(times) / len(times), launches, (sum(ar) / len(ar) if ar else 0.0), model
 
 
-def train_step_sample(dev, crop=108, iters=5, warmup=3, cpu_crop=0):
+def train_step_sample(dev, crop=108, iters=10, warmup=6, cpu_crop=0):
     """Secondary measurement (BASELINE.json configs[2], not the headline metric): one full training iteration of the
     apollo model (unet_deconv + deep_linear_gen + 4 basic Ds, batch 1, randomized projection depth 10) on a random
     crop.  Never allowed to take the headline line down: any failure is reported in place of the numbers."""
@@ -328,6 +347,10 @@ def train_step_sample(dev, crop=108, iters=5, warmup=3, cpu_crop=0):
         out = {"metric": "apollo training iteration (G_A unet_deconv + G_B deep_linear_gen + 4 PatchGAN Ds, batch 1)",
                "crop": crop, "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "iters": iters, "warmup": warmup,
                "library_calls_per_iter": launches, "losses_finite": bool(finite),
+               "ms_per_iter_synchronised": time_apollo_iterations.last_latency_ms,
+               "timing": "K iterations enqueued back to back between two CUDA events (steady-state throughput, as the "
+                         "reference's loop runs); ms_per_iter_synchronised = with a device synchronisation after every "
+                         "iteration",
                "data": "synthetic random crop, random-init weights"}
         if cpu_crop:
             out["cpu_baseline"] = train_step_cpu_baseline(cpu_crop, crop)
@@ -336,7 +359,7 @@ def train_step_sample(dev, crop=108, iters=5, warmup=3, cpu_crop=0):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def train_step_dp(dev, rank, world, barrier, crop=148, iters=5, warmup=3):
+def train_step_dp(dev, rank, world, barrier, crop=148, iters=10, warmup=6):
     """BASELINE.json configs[3]: the apollo iteration data parallel, one crop^3 per GPU, gradients of both optimisers
     averaged by one NCCL all-reduce each (the reference's only collective is DataParallel, models/networks.py:132-135).
     Every rank first runs the iteration ALONE (no process group use), then all ranks run it together; times are the

@@ -40,10 +40,15 @@ with redirect_stdout(io.StringIO()):
 torch.manual_seed(100 + rank)    # different crops
 crops = [torch.rand((1, 1, S, S, S)).pin_memory() for _ in range(3)]
 ev = lambda: torch.cuda.Event(enable_timing=True)
-times, launches = [], 0
-for i in range(iters + 3):
+# warm-up, then (a) latency: a device synchronisation after every iteration; (b) throughput: `iters` iterations
+# enqueued back to back, one synchronisation at the end (how the reference's loop runs, train_onecube.py:83-110)
+for i in range(4):
+    m.set_input({"A": crops[i % 3], "A_paths": "synthetic"})
+    m.optimize_parameters()
+torch.cuda.synchronize()
+lat = []
+for i in range(3):
     e0, e1 = ev(), ev()
-    n0 = _lib.LAUNCHES
     if world > 1:
         dist.barrier()
     e0.record()
@@ -51,10 +56,20 @@ for i in range(iters + 3):
     m.optimize_parameters()
     e1.record()
     torch.cuda.synchronize()
-    launches = _lib.LAUNCHES - n0
-    if i >= 3:
-        times.append(e0.elapsed_time(e1))
-ms = sum(times) / len(times)
+    lat.append(e0.elapsed_time(e1))
+if world > 1:
+    dist.barrier()
+e0, e1 = ev(), ev()
+n0 = _lib.LAUNCHES
+e0.record()
+for i in range(iters):
+    m.set_input({"A": crops[i % 3], "A_paths": "synthetic"})
+    m.optimize_parameters()
+e1.record()
+torch.cuda.synchronize()
+launches = (_lib.LAUNCHES - n0) // iters
+ms = e0.elapsed_time(e1) / iters
+ms_sync = sum(lat) / len(lat)
 if world > 1:
     t = torch.tensor([ms], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -62,7 +77,7 @@ if world > 1:
 flop = 3 * (unet_engine.FLOP_PER_VOXEL + deeplinear_engine.FLOP_PER_VOXEL) * S ** 3      # reference layer FLOPs, fwd + 2x bwd
 losses = m.get_current_losses()
 if rank == 0:
-  print(json.dumps({"crop": S, "n_gpus": world, "ms_per_iter": round(ms, 3),
+  print(json.dumps({"crop": S, "n_gpus": world, "ms_per_iter": round(ms, 3), "ms_per_iter_synchronised": round(ms_sync, 3),
                   "crops_per_s": round(world * 1e3 / ms, 2), "launches": launches,
                   "reference_flop_tflops": round(world * flop / ms / 1e9, 1),
                   "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
