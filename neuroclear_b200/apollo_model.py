@@ -119,7 +119,10 @@ class AxialToLateralGANApolloModel:
     # ---- :142-160
     def set_input(self, input):
         a_to_b = getattr(self.opt, "direction", "AtoB") == "AtoB"
-        self.real = input["A" if a_to_b else "B"].to(self.device)
+        src = input["A" if a_to_b else "B"]
+        # a PINNED host crop is copied asynchronously (the reference's blocking .to() drains the stream once per
+        # iteration and keeps the host from enqueueing ahead); pageable tensors keep the blocking copy
+        self.real = src.to(self.device, non_blocking=bool(getattr(src, "is_pinned", lambda: False)()))
         self.image_paths = input["A_paths" if a_to_b else "B_paths"]
         self.projection_depth = self.dpath.draw_projection_depth()
 
