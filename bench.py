@@ -310,6 +310,7 @@ def time_apollo_iterations(dev, crop, iters, warmup, distributed, rank=0, barrie
     torch.cuda.synchronize()
     lat = []
     for i in range(3):                                      # per-iteration latency (synchronised every iteration)
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         model.set_input({"A": crops[i % 2], "A_paths": "synthetic"})
@@ -317,7 +318,7 @@ def time_apollo_iterations(dev, crop, iters, warmup, distributed, rank=0, barrie
         e1.record()
         torch.cuda.synchronize()
         lat.append(e0.elapsed_time(e1))
-    time_apollo_iterations.last_latency_ms = sum(lat) / len(lat)
+    time_apollo_iterations.last_latency_ms = sorted(lat)[len(lat) // 2]      # median of three
     if barrier is not None:
         barrier()
     apollo_d_path.ALLREDUCE_EVENTS = [] if distributed else None

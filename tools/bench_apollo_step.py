@@ -69,7 +69,7 @@ e1.record()
 torch.cuda.synchronize()
 launches = (_lib.LAUNCHES - n0) // iters
 ms = e0.elapsed_time(e1) / iters
-ms_sync = sum(lat) / len(lat)
+ms_sync = sorted(lat)[len(lat) // 2]
 if world > 1:
     t = torch.tensor([ms], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
