@@ -203,15 +203,17 @@ in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ m
   const unsigned cg_per = C / 8;
   const unsigned total = static_cast<unsigned>(voxels) * cg_per;  // per cube: < 2^31 (checked by the launcher)
   const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
+  // the grid stride (gridDim.x * 256) is a multiple of C / 8 (a power of two <= 64): a thread keeps its channel group
+  const int cg = static_cast<int>((blockIdx.x * 256u + threadIdx.x) % cg_per);
+  float mu[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = __ldg(mr + cg * 8 + i);
+    rs[i] = __ldg(mr + C + cg * 8 + i);
+  }
   for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
     const unsigned vox = idx / cg_per;
-    const int cg = static_cast<int>(idx - vox * cg_per);
-    float mu[8], rs[8], o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mu[i] = __ldg(mr + cg * 8 + i);
-      rs[i] = __ldg(mr + C + cg * 8 + i);
-    }
+    float o[8];
     const long long gv = static_cast<long long>(nb) * voxels + vox;
     norm8(raw + gv * C + cg * 8, mu, rs, o);
     *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pack8<BF16>(o);
@@ -219,7 +221,7 @@ in_relu_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ m
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ mean_rstd, int D, int H, int W,
                           int C, __half* __restrict__ y, int y_ld, int y_coff,
                           __half* __restrict__ pooled) {
@@ -228,28 +230,43 @@ in_relu_pool_apply_kernel(const __half* __restrict__ raw, const float* __restric
   const int PD = D / 2, PH = H / 2, PW = W / 2;
   const unsigned total = static_cast<unsigned>(PD) * PH * PW * cg_per;  // per cube: < 2^31 (checked by the launcher)
   const float* mr = mean_rstd + static_cast<size_t>(nb) * 2 * C;
+  // the grid stride (gridDim.x * 256) is a multiple of C / 8 (a power of two <= 64): a thread keeps its channel group
+  const int cg = static_cast<int>((blockIdx.x * 256u + threadIdx.x) % cg_per);
+  float mu[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = __ldg(mr + cg * 8 + i);
+    rs[i] = __ldg(mr + C + cg * 8 + i);
+  }
   for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
-    const int cg = static_cast<int>(idx % cg_per);
     unsigned r = idx / cg_per;
     const int pw = static_cast<int>(r % PW);
     r /= PW;
     const int ph = static_cast<int>(r % PH);
     const int pd = static_cast<int>(r / PH);
-    float mu[8], rs[8];
+    // all eight 16-byte loads of the 2 x 2 x 2 window are issued before the first use
+    uint4 rawv[8];
+    const long long gv0 = ((static_cast<long long>(nb) * D + 2 * pd) * H + 2 * ph) * W + 2 * pw;
+    const long long sH = W, sD = static_cast<long long>(H) * W;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mu[i] = __ldg(mr + cg * 8 + i);
-      rs[i] = __ldg(mr + C + cg * 8 + i);
+    for (int k = 0; k < 8; ++k) {
+      const long long gv = gv0 + (k >> 2) * sD + ((k >> 1) & 1) * sH + (k & 1);
+      rawv[k] = __ldcs(reinterpret_cast<const uint4*>(raw + gv * C + cg * 8));
     }
     float mx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) mx[i] = 0.f;  // post-ReLU values are >= 0
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int dz = 2 * pd + (k >> 2), hy = 2 * ph + ((k >> 1) & 1), wx = 2 * pw + (k & 1);
-      const long long gv = ((static_cast<long long>(nb) * D + dz) * H + hy) * W + wx;
+      const __half2* h2 = reinterpret_cast<const __half2*>(&rawv[k]);
       float o[8];
-      norm8(raw + gv * C + cg * 8, mu, rs, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        o[2 * i] = fmaxf((f.x - mu[2 * i]) * rs[2 * i], 0.f);
+        o[2 * i + 1] = fmaxf((f.y - mu[2 * i + 1]) * rs[2 * i + 1], 0.f);
+      }
+      const long long gv = gv0 + (k >> 2) * sD + ((k >> 1) & 1) * sH + (k & 1);
       *reinterpret_cast<uint4*>(y + gv * y_ld + y_coff + cg * 8) = pack8<BF16>(o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], o[i]);
@@ -263,6 +280,7 @@ template <bool BF16>
 static int in_relu_apply_t(const void* raw_v, const float* mean_rstd, int NB, int D, int H, int W, int C, void* y,
                            int y_ld, int y_coff, void* pooled, cudaStream_t stream) {
   if (C % 8 || y_ld % 8 || y_coff % 8) return set_error("in_relu_apply: channel counts must be multiples of 8");
+  if (256 % (C / 8)) return set_error("in_relu_apply: C / 8 must divide 256 (a thread keeps one channel group)");
   if (NB > 65535) return set_error("in_relu_apply: NB too large");
   if (static_cast<long long>(D) * H * W * (C / 8) >= (1ll << 31)) return set_error("in_relu_apply: cube too large");
   const __half* raw = static_cast<const __half*>(raw_v);
