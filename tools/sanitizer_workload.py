@@ -38,7 +38,7 @@ fake = asm.getDict()["fake"]
 print("histogram-matched assembly", fake.shape)
 print("projections", [report.max_projection(fake, a, device=dev).shape for a in range(3)])   # (the reference's
 # hard-coded --save_projections windows are empty on a volume this small: np.amax raises there, and so do we)
-print("psnr", report.psnr_report(vol, fake, vol, dev)[:2])
+print("psnr", report.psnr_report(vol, fake, np.roll(vol, 1, 0), dev)[:2])
 mopt = Namespace(isTrain=True, gpu_ids=[0], gan_mode="lsgan", randomize_projection_depth=True, projection_depth=10,
                  min_projection_depth=2, lambda_plane=[1, 1, 1], input_nc=1, output_nc=1, ngf=64, ndf=64,
                  netG="unet_deconv", netG_B="deep_linear_gen", netD="basic", n_layers_D=3, norm="instance",
