@@ -35,6 +35,11 @@ const char* nc_last_error(void);
  * binary was compiled from (neuroclear_b200/build.py passes it as -DNC_SOURCE_HASH); build() recompiles when the
  * digest of the tree differs, so a stale shipped .so cannot pass for the source */
 const char* nc_build_source_hash(void);
+/* Asynchronous pitched host -> device copy (cudaMemcpy2DAsync; src should be pinned): `rows` segments of width_bytes,
+ * pitch_bytes apart in BOTH buffers.  Used to upload a y-range of every z-plane of a volume slab in one call, so the
+ * first cube rows start before the rest of the slab has crossed PCIe (pipeline.ChunkedUpload). */
+int nc_memcpy2d_h2d_async(void* dst, const void* src, int64_t pitch_bytes, int64_t width_bytes, int64_t rows,
+                          nc_stream_t stream);
 /* number of SMs of the current device (148 on B200); <0 on error */
 int nc_device_sm_count(void);
 /* test hook: cap the persistent grid of the tensor-core conv kernels at n CTAs (0 = one per SM) so that small test

@@ -21,6 +21,7 @@ SIGNATURES = {
     "nc_last_error": (C.c_char_p, []),
     "nc_build_source_hash": (C.c_char_p, []),
     "nc_device_sm_count": (C.c_int, []),
+    "nc_memcpy2d_h2d_async": (C.c_int, [vp, vp, i64, i64, i64, vp]),
     "nc_debug_set_max_ctas": (None, [i32]),
     "nc_debug_set_remainder_pairs": (None, [i32]),
     "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),

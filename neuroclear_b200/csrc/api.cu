@@ -20,6 +20,16 @@ const char* nc_build_source_hash(void) { return "NC_SOURCE_HASH=" NC_SOURCE_HASH
 void nc_debug_set_max_ctas(int32_t n) { debug_set_max_ctas(n); }
 void nc_debug_set_remainder_pairs(int32_t on) { debug_set_remainder_pairs(on); }
 
+int nc_memcpy2d_h2d_async(void* dst, const void* src, int64_t pitch_bytes, int64_t width_bytes, int64_t rows,
+                          nc_stream_t stream) {
+  if (rows <= 0 || width_bytes <= 0) return 0;
+  if (width_bytes > pitch_bytes) return set_error("memcpy2d: width exceeds pitch");
+  NC_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(pitch_bytes), src, static_cast<size_t>(pitch_bytes),
+                            static_cast<size_t>(width_bytes), static_cast<size_t>(rows), cudaMemcpyHostToDevice,
+                            S(stream)));
+  return 0;
+}
+
 int nc_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("no CUDA device");

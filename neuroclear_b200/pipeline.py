@@ -10,6 +10,7 @@ size because the blend always runs in ascending cube index on the slab owner.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import numpy as np
@@ -17,21 +18,25 @@ import torch
 import torch.distributed as dist
 
 from . import sharding
-from ._lib import NeuroclearError
+from ._lib import NeuroclearError, call, i64
 from .dicing import (PercentileSelect, blend_gather, dice_extract, dice_geometry, rescale_u16_crop)
 from .unet_engine import UnetDeconvEngine
 
 
 class ChunkedUpload:
-    """Input planes [z0, z0 + n) of a pinned host slab -> device slab, chunk by chunk on a copy stream.
-    ensure(z): every chunk containing planes below z has been produced by `source` (reader thread) and its H2D copy is
-    enqueued; wait_for(z): additionally makes the CURRENT stream wait for those copies."""
+    """A pinned host slab (planes [z0, z0 + n) of the volume) -> device slab, chunk by chunk on a copy stream.
+    axis 0: chunks are z-plane ranges (contiguous copies; what a file reader produces); axis 1: chunks are y-row ranges
+    of ALL planes (one pitched cudaMemcpy2DAsync each) — cubes are ordered x -> y -> z, so when a rank's cubes span
+    only one or two z-layers (8 GPUs) the first batches need every plane but only the first rows.
+    ensure(e): every chunk below coordinate e (a plane index for axis 0, a row index for axis 1) has been produced by
+    `source` (reader thread) and its H2D copy is enqueued; wait_for(e): the CURRENT stream also waits for them."""
 
-    def __init__(self, slab_host, vol_dev, z0, copy_stream, chunks, source=None):
+    def __init__(self, slab_host, vol_dev, z0, copy_stream, chunks, source=None, axis=0):
         import queue
         import threading
-        self.host, self.dev, self.z0, self.stream = slab_host, vol_dev, z0, copy_stream
-        n = slab_host.shape[0]
+        self.host, self.dev, self.stream, self.axis = slab_host, vol_dev, copy_stream, axis
+        self.z0 = z0 if axis == 0 else 0
+        n = slab_host.shape[axis]
         step = max(1, -(-n // chunks))
         self.bounds = [(a, min(n, a + step)) for a in range(0, n, step)]
         self.events = []             # one per enqueued chunk
@@ -61,7 +66,14 @@ class ChunkedUpload:
                 if got is None:
                     raise self.error
             with torch.cuda.stream(self.stream):
-                self.dev[a:b].copy_(self.host[a:b], non_blocking=True)
+                if self.axis == 0:
+                    self.dev[a:b].copy_(self.host[a:b], non_blocking=True)
+                else:       # rows [a, b) of every plane: one pitched copy (torch would stage a non-contiguous slice)
+                    nz, ny, nx = self.host.shape
+                    row = nx * self.host.element_size()
+                    call("nc_memcpy2d_h2d_async", C.c_void_p(self.dev.data_ptr() + a * row),
+                         C.c_void_p(self.host.data_ptr() + a * row), i64(ny * row), i64((b - a) * row), i64(nz),
+                         C.c_void_p(self.stream.cuda_stream))
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             self.events.append(ev)
@@ -153,9 +165,11 @@ class DicedInference:
         vol_dev = torch.empty(slab_host.shape, dtype=slab_host.dtype, device=self.device)
         self._copy_stream.wait_stream(torch.cuda.current_stream())      # the allocation above is stream-ordered
         vol_dev.record_stream(self._copy_stream)      # allocated on the compute stream, written on the copy stream
-        up = ChunkedUpload(slab_host, vol_dev, z0, self._copy_stream, chunks, source)
+        # from host memory: y-row chunks (the first cube rows start at once); from a reader: z-plane chunks (file order)
+        axis = 1 if (source is None and slab_host.is_pinned() and slab_host.is_contiguous()) else 0
+        up = ChunkedUpload(slab_host, vol_dev, z0, self._copy_stream, chunks, source, axis=axis)
         if source is None:
-            up.ensure(z1)                              # everything is already in host memory: enqueue all copies now
+            up.ensure(1 << 30)                         # everything is already in host memory: enqueue all copies now
         return vol_dev, up
 
     def infer_cubes(self, vol_dev, vol_z0, plan, queue=None, ready=None):
@@ -183,7 +197,8 @@ class DicedInference:
             k = bi % ns
             with torch.cuda.stream(lanes[k]):
                 if ready is not None:   # the uploaded chunks this batch's cubes read (border and reflection included)
-                    ready.wait_for(sharding.input_plane_range(geo, b0, b0 + nb)[1])
+                    ready.wait_for(sharding.input_plane_range(geo, b0, b0 + nb)[1] if ready.axis == 0
+                                   else sharding.input_row_end(geo, b0, b0 + nb))
                 x = dice_extract(vol_dev, vol_z0, geo, b0, nb, out=xbufs[k][:nb])
                 self.engines[k].forward(x, crop=self.border, out=queue[b0 - c0:b0 - c0 + nb], nb_cap=nbmax)
         if ns > 1:

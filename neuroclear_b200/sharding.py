@@ -48,6 +48,22 @@ def input_plane_range(geo, cube_lo: int, cube_hi: int):
     return (z0, z1) if z1 > z0 else (0, 0)
 
 
+def input_row_end(geo, cube_lo: int, cube_hi: int):
+    """One past the last ORIGINAL-volume row (y) the cubes [cube_lo, cube_hi) read — their y extent plus the border;
+    numpy-'reflect' at either end of the padded volume only maps onto rows below that bound, and rows beyond the data
+    are zero padding.  (The y analogue of input_plane_range's upper bound; the lower bound is not needed: rows are
+    uploaded in ascending order.)"""
+    if cube_hi <= cube_lo:
+        return 0
+    nz, ny, nx = geo.steps
+    lo, hi = cube_lo // nx, (cube_hi - 1) // nx               # row-of-cubes indices (z-major, then y)
+    if lo // ny != hi // ny:                                   # the range wraps into the next z-layer: every row
+        cy_max = ny - 1
+    else:
+        cy_max = hi % ny
+    return min(geo.size[1], cy_max * geo.step + geo.roi + geo.border)
+
+
 @dataclass
 class Piece:
     cube: int   # global cube index

@@ -293,3 +293,29 @@ def test_host_side_sizing_functions_of_the_training_abi(lib):
         assert b == (148 // items) * taps * 64 * 64 * 4, ks
     assert lib.nc_conv3d_wgrad_scratch_bytes(3, 1, 2, 8, 8, 256, 256) == 2 * 27 * 256 * 256 * 4     # 2 plane tiles only
     assert lib.nc_bwd_scratch_bytes(2) == 148 * 8 * 2 * 512 * 4
+
+
+def test_input_row_end_covers_every_row_a_cube_range_reads(lib):
+    """sharding.input_row_end (the bound the y-chunked upload waits for) against a brute-force enumeration of the
+    reflected / zero-padded rows every cube of the range reads."""
+    from neuroclear_b200 import sharding
+    from neuroclear_b200.dicing import dice_geometry
+    for size, roi, ov, bc in [((900, 900, 900), 120, 15, 10), ((40, 41, 58), 24, 6, 4), ((31, 40, 27), 12, 3, 2)]:
+        geo = dice_geometry(size, roi, ov, bc)
+        nz, ny, nx = geo.steps
+        P = geo.padded[1]
+        rng = np.random.default_rng(0)
+        spans = [(0, geo.n_cubes), (0, 1), (geo.n_cubes - 1, geo.n_cubes)]
+        spans += [tuple(sorted(rng.integers(0, geo.n_cubes + 1, 2))) for _ in range(40)]
+        for c0, c1 in spans:
+            if c1 <= c0:
+                continue
+            need = 0
+            for c in range(c0, c1):
+                cy = (c % (nx * ny)) // nx
+                js = np.arange(cy * geo.step - bc, cy * geo.step + roi + bc)
+                ks = np.where(js < 0, -js, np.where(js >= P, 2 * (P - 1) - js, js))
+                ks = ks[ks < size[1]]                       # rows beyond the data are zero padding, never read
+                need = max(need, int(ks.max()) + 1 if ks.size else 0)
+            got = sharding.input_row_end(geo, int(c0), int(c1))
+            assert need <= got <= size[1], (size, c0, c1, need, got)
