@@ -428,38 +428,6 @@ def workload_config(shape, gpus):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def bind_to_gpu_numa_node(local):
-    """Multi-GPU runs: pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA node its
-    GPU hangs off, so that eight ranks' H2D / D2H streams do not all cross the socket interconnect.  Best effort:
-    returns a short description, or None when the topology cannot be read."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs a 4-digit one
-            bus = bus[4:]
-        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= set(os.sched_getaffinity(0))
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return "node %d (%d cpus)" % (node, len(cpus))
-    except Exception:  # noqa: BLE001 - best effort
-        return None
-
-
 class StdoutGuard:
     """Libraries (NCCL's version banner, torch warnings) may print to fd 1; the driver wants exactly ONE JSON line
     there.  Everything written to fd 1 while the guard is active goes to stderr; emit() writes to the real stdout."""
@@ -548,7 +516,6 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N>1)" % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -688,7 +655,6 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": value / PUBLISHED_VOXELS_PER_S, "dtype": "fp16", "data": "synthetic",
             "config": workload_config(shape, world), "batch_cubes": args.batch, "streams": args.streams,
-            "host_numa_binding": numa,
             "clocks": main_res["clocks"],
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["launches"],
