@@ -107,3 +107,40 @@ def test_gradient_bucket_allreduce(tmp_path):
     world = 2
     mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("gok%d" % r)).exists() for r in range(world))
+
+
+def _digest_worker(rank, world, port, shape, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        vol = np.random.default_rng(3).integers(0, 65536, shape, dtype=np.uint16)
+        z0, z1 = shape[0] * rank // world, shape[0] * (rank + 1) // world       # any partition into plane ranges
+        if world == 3 and rank == 1:
+            z1 = z0                                                            # a rank may own no output plane at all
+        if world == 3 and rank == 2:
+            z0 = shape[0] // 3
+        digest, planes = bench.volume_digest(vol[z0:z1], z0, rank, world, torch.device("cpu"))
+        if rank == 0:
+            with open(out_path, "w") as f:
+                f.write("%s %d" % (digest, planes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_output_digest_does_not_depend_on_the_partition(tmp_path):
+    """bench.py's out_sha256 (the bit-exact multi-GPU claim): the digest of the assembled volume is the same however
+    the z-planes are split over ranks — world sizes 1, 2 and 3 (with an empty rank) over gloo."""
+    shape = (23, 17, 31)
+    got = []
+    for world in (1, 2, 3):
+        out = str(tmp_path / ("digest_%d.txt" % world))
+        mp.spawn(_digest_worker, args=(world, _free_port(), shape, out), nprocs=world, join=True)
+        got.append(open(out).read())
+    assert got[0] == got[1] == got[2] and got[0].endswith(" 23")
+    import hashlib
+    vol = np.random.default_rng(3).integers(0, 65536, shape, dtype=np.uint16)
+    h = hashlib.sha256()
+    for z in range(shape[0]):
+        h.update(hashlib.sha256(vol[z].tobytes()).digest())
+    assert got[0].split()[0] == h.hexdigest()
