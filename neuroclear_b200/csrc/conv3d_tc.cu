@@ -680,7 +680,7 @@ __device__ __forceinline__ RpCoord decode_rp(const ConvTcArgs& a, int tile) {
   return t;
 }
 
-template <int BN, bool XF>
+template <int BN, bool XF, bool BF16 = false>
 __global__ void __launch_bounds__(XF ? 384 : 256, 1)
 conv3d_rp_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs args) {
   using C = RpCfg<BN>;
@@ -772,7 +772,8 @@ conv3d_rp_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform loops, one elected lane)
-    constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN);
+    constexpr uint32_t FMT = BF16 ? ((1u << 7) | (1u << 10)) : 0u;  // A / B operand format: 0 = fp16, 1 = bf16
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, BN) | FMT;
     constexpr uint32_t A_HI = ((C::HALO_W * 128u) >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t LO_FLAGS = 1u << 16;
@@ -907,41 +908,46 @@ conv3d_rp_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvTcArgs arg
                 args.out_raw + (((static_cast<size_t>(t.nb) * args.D + d) * args.H + h) * args.W + w) * args.ldo + co);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_half2_sat(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
-                                  pack_half2_sat(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
-                                  pack_half2_sat(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
-                                  pack_half2_sat(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
+              dst[i] = make_uint4(pack_pair<BF16>(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
+                                  pack_pair<BF16>(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
+                                  pack_pair<BF16>(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
+                                  pack_pair<BF16>(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
           }
-          float v[32], v2[32];
+          if constexpr (!BF16) {
+            float v[32], v2[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = valid ? __uint_as_float(raw[i]) : 0.f;
-            v[i] = x;
-            v2[i] = x * x;
+            for (int i = 0; i < 32; ++i) {
+              const float x = valid ? __uint_as_float(raw[i]) : 0.f;
+              v[i] = x;
+              v2[i] = x * x;
+            }
+            csum[cc] += warp_colsum32(v, lane);
+            csq[cc] += warp_colsum32(v2, lane);
           }
-          csum[cc] += warp_colsum32(v, lane);
-          csq[cc] += warp_colsum32(v2, lane);
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&accEmpty[buf]);
 
-      float* mine = statScratch + q * 2 * BN;
+      if constexpr (!BF16) {
+        float* mine = statScratch + q * 2 * BN;
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        mine[cc * 32 + lane] = csum[cc];
-        mine[BN + cc * 32 + lane] = csq[cc];
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          mine[cc * 32 + lane] = csum[cc];
+          mine[BN + cc * 32 + lane] = csq[cc];
+        }
+        ptx::named_bar_sync(1, 128);
+        const int e = threadIdx.x - 128;
+        for (int i = e; args.stats_partial != nullptr && i < 2 * BN; i += 128) {
+          const float s =
+              (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
+          const int which = i / BN, col = i - which * BN;
+          args.stats_partial[(static_cast<size_t>(t.spatial + (t.nb + 1) * args.stats_tile0) * 2 + which) * args.ldo +
+                             t.n_tile * BN + col] = s;
+        }
+        ptx::named_bar_sync(1, 128);
       }
-      ptx::named_bar_sync(1, 128);
-      const int e = threadIdx.x - 128;
-      for (int i = e; args.stats_partial != nullptr && i < 2 * BN; i += 128) {
-        const float s = (statScratch[i] + statScratch[2 * BN + i]) + (statScratch[4 * BN + i] + statScratch[6 * BN + i]);
-        const int which = i / BN, col = i - which * BN;
-        args.stats_partial[(static_cast<size_t>(t.spatial + (t.nb + 1) * args.stats_tile0) * 2 + which) * args.ldo +
-                           t.n_tile * BN + col] = s;
-      }
-      ptx::named_bar_sync(1, 128);
     }
   }
 
@@ -1102,11 +1108,11 @@ size_t conv3d_k3_stats_tiles(int NB, int D, int H, int W, int Cout) {
   return static_cast<size_t>(NB) * ((D + td - 1) / td) * ((H + TH - 1) / TH) * tw;
 }
 
-template <int BN>
+template <int BN, bool BF16 = false>
 static int launch_rp(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) {
   using C = RpCfg<BN>;
   CUtensorMap tm;
-  if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::LINES)) return rc;
+  if (int rc = make_act_tmap(&tm, x, Cin, a.W, a.H, a.D, a.NB, C::HALO_W, C::LINES, BF16)) return rc;
   a.tiles_w = (a.W + TW - 1) / TW;
   a.tiles_h = 1;
   a.tiles_d = (a.D + 3) / 4;
@@ -1115,7 +1121,13 @@ static int launch_rp(const void* x, ConvTcArgs a, int Cin, cudaStream_t stream) 
   const int cap = (g_max_ctas > 0 && g_max_ctas < num_sms()) ? g_max_ctas : num_sms();
   const int grid = a.total_tiles < cap ? a.total_tiles : cap;
   static bool attr_set[2][64] = {{false}};
-  if (a.in_mr) {
+  if constexpr (BF16) {
+    auto kern = conv3d_rp_kernel<BN, false, true>;
+    static bool attr_bf16[64] = {false};
+    if (first_use_on_device(attr_bf16))
+      NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tm, a);
+  } else if (a.in_mr) {
     auto kern = conv3d_rp_kernel<BN, true>;
     if (first_use_on_device(attr_set[1]))
       NC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1180,6 +1192,16 @@ int conv3d_k3_dgrad(const void* dy, int NB, int D, int H, int W, int Cout, const
   }
   if (Cin % 128) return set_error("conv3d_k3_dgrad: Cin must be 64 or a multiple of 128");
   a.n_tiles = Cin / 128;
+  if (const int rem = rp_rem(H, Cin)) {   // remainder pairs, as in conv3d_k3_fwd (no statistics here)
+    const int full = H / TH;
+    if (full > 0) {
+      a.tiles_h_cap = full;
+      if (int rc = launch_cfg<3, 128, 2, 0, false, true>(dy, a, Cout, stream)) return rc;
+    }
+    a.tiles_h_cap = 0;
+    a.rp_h0 = full * TH, a.rp_rem = rem;
+    return launch_rp<128, true>(dy, a, Cout, stream);
+  }
   return launch_cfg<3, 128, 2, 0, false, true>(dy, a, Cout, stream);
 }
 

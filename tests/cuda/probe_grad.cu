@@ -48,6 +48,7 @@ static const Case cases[] = {
     {"k5_64_64", 5, 1, 6, 21, 13, 64, 64},      {"k3_64_64_big", 3, 1, 24, 40, 40, 64, 64},
     {"k3_128_128_t", 3, 1, 54, 54, 54, 128, 128}, {"k3_64_64_t", 3, 1, 108, 108, 108, 64, 64},
     {"k5_64_64_t", 5, 1, 108, 108, 108, 64, 64},  {"k3_256_256_t", 3, 1, 27, 27, 27, 256, 256},
+    {"k3_128_128_rp", 3, 2, 7, 22, 20, 128, 128}, {"k3_256_256_l2", 3, 1, 9, 37, 37, 256, 256},
 };
 static const int ncases = sizeof(cases) / sizeof(cases[0]);
 
@@ -224,6 +225,7 @@ static int run_time(const Case& c, int iters) {
 }
 
 int main(int argc, char** argv) {
+  if (getenv("NC_RP")) nc_debug_set_remainder_pairs(atoi(getenv("NC_RP")));   // 0: regular tiles only
   if (argc < 3) {
     printf("usage: probe_grad dgrad|wgrad|time <case> ...\n");
     return 1;

@@ -12,7 +12,7 @@ for c in 0 1 2 3 4 5; do
     timeout 120 $P wgrad $c $f >> $LOG 2>&1 || echo "wgrad case $c fmt $f exit=$?" >> $LOG
   done
 done
-for c in 0 1 2 3 5; do
+for c in 0 1 2 3 5 10 11; do
   timeout 120 $P dgrad $c >> $LOG 2>&1 || echo "dgrad case $c exit=$?" >> $LOG
 done
 if [ "$1" != "notime" ]; then
