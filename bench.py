@@ -395,7 +395,9 @@ def train_step_dp(dev, rank, world, barrier, crop=148, iters=10, warmup=6):
             del model
             torch.cuda.empty_cache()
             ms_dp, _, ar, model = time_apollo_iterations(dev, crop, iters, warmup, True, rank, barrier)
-            ms_dp, ar = rmax(ms_dp), rmax(ar)
+            ms_dp, ar_wait = rmax(ms_dp), rmax(ar)
+            ar = -rmax(-ar)       # min over ranks: the last rank to arrive measures the collective itself; the others
+            #                       also measure how long they waited for it (GPU-to-GPU speed differences)
             same = True
             for opt_ in model.optimizers:
                 flat = torch.cat([p.detach().reshape(-1) for p in opt_.params])
@@ -404,6 +406,7 @@ def train_step_dp(dev, rank, world, barrier, crop=148, iters=10, warmup=6):
                 dist.all_reduce(hi, op=dist.ReduceOp.MAX)
                 same = same and bool(torch.equal(lo, hi))
             out.update({"ms_per_iter": ms_dp, "crops_per_s": world * 1e3 / ms_dp, "allreduce_ms_per_iter": ar,
+                        "allreduce_ms_per_iter_incl_wait_max": ar_wait,
                         "allreduce_bytes_per_iter": 4 * sum(p.numel() for o in model.optimizers for p in o.params),
                         "weak_scaling_efficiency": ms_alone / ms_dp, "weights_identical_across_ranks": same})
         out["losses_finite"] = bool(all(np.isfinite(v) for v in model.get_current_losses().values()))
