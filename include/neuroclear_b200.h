@@ -48,6 +48,9 @@ void nc_debug_set_max_ctas(int32_t n);
 /* test / measurement hook: 0 disables the remainder-pair kernel of the N-tile-128 k3 convolutions (the last, partly
  * filled 16-line h-tile is then computed by the regular kernel); the stored values are identical either way */
 void nc_debug_set_remainder_pairs(int32_t on);
+/* test / measurement hook: 1, 2, 4 or 8 force the thread-block-cluster size (= split of the reduction dimension) of
+ * the PatchGAN convolutions nc_conv2d_k4_*; 0 restores the cost model.  Results agree up to fp32 summation order. */
+void nc_debug_set_disc_cluster(int32_t c);
 
 /* ---- dicing geometry (host-only integer math) --------------------------------------------------------------
  * util/util.py:196-215 pad_for_dicing  +  data/diceImage_dataset.py:82-106 DiceCube.__init__/indexToCoordinates

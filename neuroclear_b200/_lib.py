@@ -24,6 +24,7 @@ SIGNATURES = {
     "nc_memcpy2d_h2d_async": (C.c_int, [vp, vp, i64, i64, i64, vp]),
     "nc_debug_set_max_ctas": (None, [i32]),
     "nc_debug_set_remainder_pairs": (None, [i32]),
+    "nc_debug_set_disc_cluster": (None, [i32]),
     "nc_dice_geometry": (i64, [I3, i32, i32, I3, I3]),
     "nc_dice_extract_u16": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),
     "nc_dice_extract_u8": (C.c_int, [vp, i32, i32, I3, I3, I3, i32, i32, i32, i64, i32, vp, vp]),

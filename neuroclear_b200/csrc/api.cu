@@ -19,6 +19,7 @@ const char* nc_build_source_hash(void) { return "NC_SOURCE_HASH=" NC_SOURCE_HASH
 
 void nc_debug_set_max_ctas(int32_t n) { debug_set_max_ctas(n); }
 void nc_debug_set_remainder_pairs(int32_t on) { debug_set_remainder_pairs(on); }
+void nc_debug_set_disc_cluster(int32_t c) { debug_set_disc_cluster(c); }
 
 int nc_memcpy2d_h2d_async(void* dst, const void* src, int64_t pitch_bytes, int64_t width_bytes, int64_t rows,
                           nc_stream_t stream) {

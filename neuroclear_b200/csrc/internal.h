@@ -115,6 +115,7 @@ int mip_fwd(const float* vol, int D, int H, int W, int axis, int start, int dept
 int mip_bwd(const float* gproj, const int* argmax, int D, int H, int W, int axis, float* gvol, cudaStream_t stream);
 
 // disc2d.cu
+void debug_set_disc_cluster(int c);
 int conv2d_k4_fwd(const float* x, const float* w, const float* b, int N, int Cin, int H, int W, int Cout, int stride,
                   float slope, float* y, cudaStream_t stream);
 int conv2d_k4_dgrad(const float* dy, const float* w, int N, int Cin, int H, int W, int Cout, int stride, float* dx,

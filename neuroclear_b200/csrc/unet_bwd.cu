@@ -194,23 +194,34 @@ in_bwd_apply_kernel(const InBwdArgs a) {
   }
 }
 
-// out[nb][c] = scale * sum over rows of partial[nb][row][c]; fp64, fixed order (8 row lanes, then lanes in order)
-__global__ void __launch_bounds__(256)
+// out[nb][c] = scale * sum over rows of partial[nb][row][c]; fp64, fixed order (32 row lanes, then lanes in order).
+// This kernel sits between the two passes of every InstanceNorm backward (15 launches per training iteration): with 8
+// row lanes and a rolled loop it was a chain of ~75 dependent L2 round trips (33 us); 32 lanes and eight loads in
+// flight per lane make it a few microseconds.
+__global__ void __launch_bounds__(1024)
 colsum_finalize_kernel(const float* __restrict__ partial, int rows, int C, double scale, float* __restrict__ out) {
-  __shared__ double red[8][32];
+  __shared__ double red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx, nb = blockIdx.y;
   double s = 0.0;
   if (c < C) {
-    const float* p = partial + static_cast<size_t>(nb) * rows * C;
-    for (int r = ty; r < rows; r += 8) s += static_cast<double>(p[static_cast<size_t>(r) * C + c]);
+    const float* p = partial + static_cast<size_t>(nb) * rows * C + c;
+    int r = ty;
+    for (; r + 7 * 32 < rows; r += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(p + static_cast<size_t>(r + 32 * u) * C);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += static_cast<double>(v[u]);
+    }
+    for (; r < rows; r += 32) s += static_cast<double>(__ldg(p + static_cast<size_t>(r) * C));
   }
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && c < C) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    for (int i = 0; i < 32; ++i) t += red[i][tx];
     out[static_cast<size_t>(nb) * C + c] = static_cast<float>(t * scale);
   }
 }
@@ -506,7 +517,7 @@ int in_relu_bwd(const void* raw, const float* mean_rstd, int NB, int D, int H, i
                          : launch_in_bwd<2>(a, NB, pass == 1, blocks, stream);
     if (rc) return rc;
     if (pass == 0) {
-      colsum_finalize_kernel<<<dim3((2 * C + 31) / 32, NB), 256, 0, stream>>>(
+      colsum_finalize_kernel<<<dim3((2 * C + 31) / 32, NB), 1024, 0, stream>>>(
           scratch, blocks, 2 * C, 1.0 / (static_cast<double>(D) * H * W), m12);
       NC_CUDA(cudaGetLastError());
     }
@@ -522,7 +533,7 @@ int head_bwd(const void* raw, const float* mean_rstd, const float* hp, const flo
   head_bwd_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(static_cast<const __half*>(raw), mean_rstd, hp, dout,
                                                         static_cast<unsigned>(D) * H * W, du, scratch);
   NC_CUDA(cudaGetLastError());
-  colsum_finalize_kernel<<<dim3((HEAD_COLS + 31) / 32, 1), 256, 0, stream>>>(scratch, blocks * NB, HEAD_COLS, 1.0,
+  colsum_finalize_kernel<<<dim3((HEAD_COLS + 31) / 32, 1), 1024, 0, stream>>>(scratch, blocks * NB, HEAD_COLS, 1.0,
                                                                              grads);
   NC_CUDA(cudaGetLastError());
   return 0;
@@ -549,7 +560,7 @@ int conv1_wgrad(const float* x, const void* dy, int dy_fmt, int NB, int D, int H
         x, static_cast<const uint16_t*>(dy), D, H, W, ty, tx, tz * ty * tx, scratch);
   }
   NC_CUDA(cudaGetLastError());
-  colsum_finalize_kernel<<<dim3(1728 / 32, 1), 256, 0, stream>>>(scratch, blocks * NB, 1728, 1.0, dw);
+  colsum_finalize_kernel<<<dim3(1728 / 32, 1), 1024, 0, stream>>>(scratch, blocks * NB, 1728, 1.0, dw);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -573,7 +584,7 @@ int colsum_bf16(const void* src, int ld, int coff, int NB, long long rows, int C
   colsum_bf16_kernel<<<dim3(blocks, NB), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), ld, coff,
                                                            static_cast<unsigned>(rows), C, scratch);
   NC_CUDA(cudaGetLastError());
-  colsum_finalize_kernel<<<dim3((C + 31) / 32, 1), 256, 0, stream>>>(scratch, blocks * NB, C, 1.0, out);
+  colsum_finalize_kernel<<<dim3((C + 31) / 32, 1), 1024, 0, stream>>>(scratch, blocks * NB, C, 1.0, out);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
