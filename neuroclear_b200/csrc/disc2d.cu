@@ -448,6 +448,86 @@ conv2d_k4_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w
       }
 }
 
+// Stride 2: an input pixel (h, w) is reached only through the taps kh = (h + 1) % 2 (+ 2), kw = (w + 1) % 2 (+ 2) —
+// 4 of 16 — so the generic kernel above multiplies 75 % zeros.  Here the image is split into its four parity classes
+// (h % 2, w % 2); per class: M = the class's pixels, K = (co, the 4 valid taps) = Cout / 4 chunks instead of Cout.
+// Same loader roles, stage layout and reduction as above; grid.x = 4 classes x M tiles x cluster size.
+__global__ void __launch_bounds__(CONV_THREADS)
+conv2d_k4_dgrad_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w, int Cin, int H, int W, int Cout,
+                          int Ho, int Wo, int mt_class, float* __restrict__ dx) {
+  extern __shared__ __align__(16) uint8_t conv_smem[];
+  Stage* stages = reinterpret_cast<Stage*>(conv_smem);
+  float* slots = reinterpret_cast<float*>(conv_smem);
+  const unsigned rank = cluster_rank_x(), csize = cluster_size_x();
+  const int group = threadIdx.x / GT, t = threadIdx.x % GT;
+  const TilePos tp(t);
+  const int tile = blockIdx.x / csize;
+  const int cls = tile / mt_class, p0 = (tile - cls * mt_class) * TB;
+  const int ph = cls >> 1, pw = cls & 1;                  // parity of (h, w)
+  const int kh0 = (ph + 1) & 1, kw0 = (pw + 1) & 1;       // first valid tap; the other one is + 2
+  const int Hq = (H - ph + 1) / 2, Wq = (W - pw + 1) / 2;  // pixels of this class
+  const int Pq = Hq * Wq;
+  const int ci0 = blockIdx.y * TB, n = blockIdx.z;
+  // loader roles: A: class pixel t % 64, output channel (t / 64) of the chunk, its 4 valid taps;
+  //               B: input channel t / 4, output channel (t % 4) of the chunk, the same 4 taps
+  const int ap = p0 + (t & 63), aco = t >> 6;
+  const int ai = ap / Wq, aj = ap - ai * Wq;
+  const int ah = 2 * ai + ph, aw = 2 * aj + pw;
+  int offA[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int th = ah + 1 - (kh0 + 2 * (j >> 1)), tw = aw + 1 - (kw0 + 2 * (j & 1));  // even by construction
+    const bool ok = ap < Pq && th >= 0 && (th >> 1) < Ho && tw >= 0 && (tw >> 1) < Wo;
+    offA[j] = ok ? (th >> 1) * Wo + (tw >> 1) : -1;
+  }
+  const int bci = ci0 + (t >> 2), bco = t & 3;
+  int offB[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) offB[j] = (kh0 + 2 * (j >> 1)) * 4 + kw0 + 2 * (j & 1);
+  const float* dyn = dy + static_cast<size_t>(n) * Cout * Ho * Wo;
+  int kb, ke;
+  k_range((Cout + 3) / 4, rank, csize, group, kb, ke);
+  Acc acc = {};
+  k_loop(
+      kb, ke, stages + 2 * group, group, tp, acc,
+      [&](int c, Regs& r) {
+        const int coa = 4 * c + aco, cob = 4 * c + bco;
+        const float* dr = dyn + static_cast<size_t>(coa) * Ho * Wo;
+        const float* wr = w + (static_cast<size_t>(cob) * Cin + bci) * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r.a[j] = ldg_or_zero(dr + offA[j], offA[j] >= 0 && coa < Cout);
+          r.b[j] = ldg_or_zero(wr + offB[j], bci < Cin && cob < Cout);
+        }
+      },
+      [&](Stage& s, const Regs& r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s.put_a(aco * 4 + j, t & 63, r.a[j]);
+          s.put_b(bco * 4 + j, t >> 2, r.b[j]);
+        }
+      });
+  combine_groups(acc, slots, group, t);
+  cluster_reduce(acc, slots, rank, csize, group, t);
+  if (rank != 0 || group != 0) return;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int r = 0; r < 4; r += 2) {  // rows of this thread: r = 0, 1 share a row, r = 2, 3 the row + 8
+      const int p = p0 + tp.row(mi, r);
+      if (p >= Pq) continue;
+      const int i = p / Wq, j = p - i * Wq;
+      const size_t pix = static_cast<size_t>(2 * i + ph) * W + 2 * j + pw;
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ci = ci0 + tp.col(ni, r + e);
+          if (ci < Cin) dx[(static_cast<size_t>(n) * Cin + ci) * H * W + pix] = acc[mi][ni][r + e];
+        }
+    }
+}
+
 // Cin = 1 (gradient of the PatchGAN's first layer w.r.t. the image, needed by the generator losses): as a tile
 // problem 63 of 64 columns idle (57-166 us on 108 x 108 images).  Here: a block owns 64 image pixels, its four
 // quarters split the output channels (ascending inside a quarter) and are added in quarter order -> deterministic;
@@ -704,7 +784,15 @@ int conv2d_k4_dgrad(const float* dy, const float* w, int N, int Cin, int H, int 
     NC_CUDA(cudaGetLastError());
     return 0;
   }
-  const int mt = (H * W + TB - 1) / TB, nt = (Cin + TB - 1) / TB;
+  const int nt = (Cin + TB - 1) / TB;
+  if (stride == 2) {
+    const int mtq = (((H + 1) / 2) * ((W + 1) / 2) + TB - 1) / TB;  // M tiles of the largest parity class
+    const int cl = pick_cluster(4ll * mtq * nt * N, (Cout + 3) / 4);
+    static bool attr2[64] = {false};
+    return launch_conv(conv2d_k4_dgrad_s2_kernel, attr2, dim3(4 * mtq * cl, nt, N), cl, stream, dy, w, Cin, H, W, Cout,
+                       Ho, Wo, mtq, dx);
+  }
+  const int mt = (H * W + TB - 1) / TB;
   const int cl = pick_cluster(static_cast<long long>(mt) * nt * N, Cout);
   static bool attr[64] = {false};
   return launch_conv(conv2d_k4_dgrad_kernel, attr, dim3(mt * cl, nt, N), cl, stream, dy, w, Cin, H, W, Cout, Ho, Wo,

@@ -3,6 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 bash tests/cuda/run_probe_disc.sh 0 > /dev/null
+python tools/debug_disc_grad.py 2>&1 | tail -5
 python -m pytest tests/test_gpu_discriminator.py tests/test_gpu_apollo_d_path.py tests/test_gpu_siblings.py tests/test_gpu_apollo_step.py -q -x --timeout 1500 2>&1 | tail -6
 python tools/bench_apollo_step.py 108 10 2>/dev/null | tail -1
 python - <<PY
