@@ -23,16 +23,17 @@ namespace nc {
 //     (~2^-21 relative per product; the fp32 fixtures of tests/test_gpu_discriminator.py hold with unchanged
 //     tolerances);
 //   * the images are tiny (M = 121..2916 pixels) while K reaches 8192, so a layer has only 2..46 output tiles: the K
-//     range of a tile is SPLIT ACROSS A THREAD-BLOCK CLUSTER (up to 8 CTAs) and, inside each CTA, across TWO warp
-//     groups that run independent pipelines (own stages, own named barrier).  Partial tiles are summed group 0 + group
-//     1, then by the cluster's rank 0 through distributed shared memory in rank order -> bitwise repeatable, no
-//     scratch buffer;
+//     range of a tile is SPLIT ACROSS A THREAD-BLOCK CLUSTER (up to 8 CTAs).  Partial tiles are summed by the
+//     cluster's rank 0 through distributed shared memory in rank order -> bitwise repeatable, no scratch buffer.
+//     (NC_DISC_GROUPS = 2 additionally splits a CTA's range over two warp groups with independent pipelines — own
+//     stages, own named barrier, summed group 0 + group 1.  Measured: no gain, the SM's legacy-MMA rate is the bound;
+//     off by default.)
 //   * a pipeline keeps PF chunks in flight in registers (the loads are volatile asm: ptxas otherwise sinks them to
 //     the end of the loop body, next to their use) and double buffers its stage (one barrier per chunk).
-// History (tests/cuda/probe_disc.cu, profiles/r02_probe_disc_*.log): the round-1 kernels were 4 x 4 register-tiled FFMA
-// loops whose time was proportional to the chunks per CTA at ~1 us per chunk, warm or cold cache — 32 LDS.128 per 256
-// FFMA per thread saturate the shared-memory pipe.  ncu on the first mma version: 31 % issue slots busy with one
-// 8-warp CTA per SM, 19 % of the stall samples on the first use of a prefetched register.
+// History (tests/cuda/probe_disc.cu, profiles/r02_probe_disc_final.log): the round-1 kernels were
+// 4 x 4 register-tiled FFMA loops whose time was proportional to the chunks per CTA at ~1 us per chunk, warm or cold
+// cache — 32 LDS.128 per 256 FFMA per thread saturate the shared-memory pipe.  The mma form is NOT faster on a B200:
+// HMMA.1688.F32.TF32 sustains one MMA per ~5.6 clk per SM, 192 MMAs per chunk = 0.58 us whatever the occupancy.
 constexpr int TB = 64;  // tile edge (M and N)
 constexpr int KB = 16;  // K chunk
 constexpr int PF = 4;   // chunks in flight (register prefetch depth)

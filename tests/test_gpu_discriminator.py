@@ -111,3 +111,55 @@ def test_l1_loss(cuda):
     lo = torch.nn.functional.l1_loss(ac, b) * 5.0
     lo.backward()
     assert abs(loss.item() - lo.item()) <= 1e-5 * lo.item() and torch.allclose(ad.grad.cpu(), ac.grad, atol=1e-9)
+
+
+def _conv_case(cuda, n, cin, cout, h, w, stride, seed):
+    """nc_conv2d_k4_fwd / _dgrad / _wgrad alone against torch's fp32 CPU conv2d and its autograd; relative max errors."""
+    from neuroclear_b200._lib import call, ptr, stream_ptr, f32
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, 4, 4), generator=g) * 0.1
+    b = torch.randn((cout,), generator=g)
+    xc, wc, bc = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yc = torch.nn.functional.conv2d(xc, wc, bc, stride=stride, padding=1)
+    dy = torch.randn(yc.shape, generator=g)
+    yc.backward(dy)
+    xd, wd, bd, dyd = x.to(cuda), wt.to(cuda), b.to(cuda), dy.to(cuda)
+    y = torch.empty(yc.shape, device=cuda)
+    dx, dw, db = torch.empty_like(xd), torch.empty_like(wd), torch.empty_like(bd)
+    s = stream_ptr()
+    call("nc_conv2d_k4_fwd", ptr(xd), ptr(wd), ptr(bd), n, cin, h, w, cout, stride, f32(1.0), ptr(y), s)
+    call("nc_conv2d_k4_dgrad", ptr(dyd), ptr(wd), n, cin, h, w, cout, stride, ptr(dx), s)
+    call("nc_conv2d_k4_wgrad", ptr(xd), ptr(dyd), n, cin, h, w, cout, stride, ptr(dw), ptr(db), s)
+    rel = lambda a, ref: (a.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    return (rel(y, yc.detach()), rel(dx, xc.grad), rel(dw, wc.grad), rel(db, bc.grad)), (y, dx, dw)
+
+
+# (n, cin, cout, h, w, stride): the five layers of the 'basic' PatchGAN incl. odd image sizes (parity classes of
+# different size in the stride-2 data gradient), the Cout = 1 / Cin = 1 kernels and channel counts off the tile size
+CONV_CASES = [(2, 1, 64, 37, 52, 2), (1, 64, 128, 27, 23, 2), (2, 128, 256, 13, 14, 2), (1, 256, 512, 13, 13, 1),
+              (3, 512, 1, 12, 9, 1), (1, 24, 40, 19, 21, 2), (1, 70, 6, 9, 10, 1)]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_k4_kernels_vs_torch(cuda, case):
+    errs, _ = _conv_case(cuda, *case, seed=sum(case))
+    assert max(errs) <= 2e-5, (case, errs)      # 3xTF32 with chunk-wise fp32 accumulation: measured <= 3e-6
+
+
+def test_conv2d_k4_cluster_size_only_changes_summation_order(cuda, lib):
+    """The split of the reduction over a thread-block cluster (debug hook) must not change the result beyond fp32
+    summation order — long single-CTA reductions were 1e-3..3e-2 off before the chunk-wise accumulation."""
+    case = (2, 128, 256, 27, 27, 2)
+    try:
+        outs = []
+        for c in (1, 2, 4, 8, 0):
+            lib.nc_debug_set_disc_cluster(c)
+            errs, res = _conv_case(cuda, *case, seed=5)
+            assert max(errs) <= 2e-5, (c, errs)
+            outs.append(res)
+    finally:
+        lib.nc_debug_set_disc_cluster(0)
+    for res in outs[1:]:
+        for a, b in zip(res, outs[0]):
+            assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item()
