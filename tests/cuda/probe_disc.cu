@@ -2,7 +2,7 @@
 // 108^3 crop.  Built twice by tests/cuda/run_probe_disc.sh: against the tree's disc2d.cu and (-DOLD) against the
 // previous revision, so a change is measured A/B in one GPU call.  Per layer and direction: warm time (50 launches
 // back to back between two events) and cold time (L2 flushed before every launch, single-launch events, min of 5).
-//   usage: probe_disc [cluster override 0|1|2|4|8]
+//   usage: probe_disc [cluster override 0|1|2|4|8] [quick]   (quick: one launch per case, for compute-sanitizer)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -24,8 +24,16 @@
 
 struct Layer { int cin, cout, h, stride; };
 
+static bool g_quick = false;  // one launch per case, no timing (compute-sanitizer runs)
+
 template <class F>
 static int time_it(const char* tag, F f, float* flush, size_t flush_bytes) {
+  if (g_quick) {
+    if (f()) { printf("%s: %s\n", tag, nc::last_error()); return 1; }
+    CK(cudaDeviceSynchronize());
+    printf("%-28s ran\n", tag);
+    return 0;
+  }
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a));
   CK(cudaEventCreate(&b));
@@ -57,11 +65,13 @@ int main(int argc, char** argv) {
 #ifndef OLD
   if (argc > 1) nc::debug_set_disc_cluster(atoi(argv[1]));
 #endif
+  g_quick = argc > 2;
   const Layer L[5] = {{1, 64, 108, 2}, {64, 128, 54, 2}, {128, 256, 27, 2}, {256, 512, 13, 1}, {512, 1, 12, 1}};
   const size_t flush_bytes = 512u << 20;
   float* flush;
   CK(cudaMalloc(&flush, flush_bytes));
   for (int N : {1, 2, 4}) {
+    if (g_quick && N == 4) break;
     for (int l = 0; l < 5; ++l) {
       const Layer& y = L[l];
       const int ho = (y.h - 2) / y.stride + 1;
