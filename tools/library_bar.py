@@ -147,7 +147,9 @@ def training_bar(crop, iters):
         def step():
             model.set_input({"A": real, "A_paths": "synthetic"})
             model.optimize_parameters()
-        return _time(step, iters, warmup=3)
+        # 6 warm-up iterations: the caching allocator (side-stream record_stream) needs a few iterations before the
+        # timed region stops calling cudaMalloc (bench.py's train_step uses the same count)
+        return _time(step, iters, warmup=6)
 
     with contextlib.redirect_stdout(io.StringIO()):
         ref = RefModel(Namespace(gpu_ids=[0], **base))
