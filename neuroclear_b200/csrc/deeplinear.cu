@@ -28,56 +28,94 @@ __device__ __forceinline__ uint16_t to_bits(float v, int fmt) {
   return *reinterpret_cast<const uint16_t*>(&h);
 }
 
+// im2col49 / col2im49 work on in-plane tiles of 8 (h) x 32 (w) voxels whose 3-voxel halo is staged in shared memory.
+// (The round-1 kernels went to L1 / L2 for every element — 49 two-byte gathers from 49 different 128-byte rows per
+// voxel in col2im, a full index decode per 16 bytes written in im2col — and ran at 0.22 / 0.10 ms per 108^3 crop; the
+// HBM bound of the 128 bytes per voxel they move is 0.03 ms.)
+namespace ic {
+constexpr int TY = 8, TX = 32, HY = TY + 6, HX = TX + 6, ROWS = HY * HX;  // 532 halo voxels
+constexpr int PITCH = 33;  // words per staged row in col2im (28 used = 56 channels): odd -> conflict-free gathers
+constexpr int COL2IM_SMEM = ROWS * PITCH * 4;
+}  // namespace ic
+
 // out[v][kh * 7 + kw] = x[d][h + kh - 3][w + kw - 3] (zero outside the plane), channels 49..63 = 0
+// thread = one 8-channel group (16 bytes) of 8 voxels of the tile; 8 consecutive lanes write one voxel's 128 bytes
 __global__ void __launch_bounds__(256)
-im2col49_kernel(const float* __restrict__ x, int D, int H, int W, int fmt, uint16_t* __restrict__ out) {
+im2col49_kernel(const float* __restrict__ x, int D, int H, int W, int tiles_y, int tiles_x, int fmt,
+                uint16_t* __restrict__ out) {
+  using namespace ic;
+  __shared__ float xs[ROWS];
   const int nb = blockIdx.y;
-  const unsigned total = static_cast<unsigned>(D) * H * W * 8;
-  const float* xc = x + static_cast<size_t>(nb) * D * H * W;
-  for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
-    const int g = idx & 7;
-    const unsigned v = idx >> 3;
-    const int w = v % W;
-    const unsigned r = v / W;
-    const int h = r % H, d = r / H;
+  const int tx = blockIdx.x % tiles_x;
+  const int r = blockIdx.x / tiles_x;
+  const int d = r / tiles_y, h0 = (r % tiles_y) * TY, w0 = tx * TX;
+  const float* xp = x + (static_cast<size_t>(nb) * D + d) * H * W;
+  for (int i = threadIdx.x; i < ROWS; i += 256) {
+    const int zh = h0 + i / HX - 3, zw = w0 + i % HX - 3;
+    xs[i] = (zh >= 0 && zh < H && zw >= 0 && zw < W) ? __ldg(xp + static_cast<size_t>(zh) * W + zw) : 0.f;
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 7;
+  int off[8];  // offset of channel g * 8 + i inside the staged tile relative to the voxel, -1 for the 15 zero channels
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    off[i] = c < 49 ? (c / 7) * HX + c % 7 : -1;
+  }
+  uint16_t* op = out + ((static_cast<size_t>(nb) * D + d) * H * W) * 64 + g * 8;
+#pragma unroll 2
+  for (int j = 0; j < 8; ++j) {
+    const int v = (threadIdx.x >> 3) + 32 * j;  // voxel of the tile: ly = j, lx = threadIdx.x / 8
+    const int ly = v / TX, lx = v % TX;
+    if (h0 + ly >= H || w0 + lx >= W) continue;
+    const float* base = xs + ly * HX + lx;
     uint16_t o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = g * 8 + i;
-      const int kh = c / 7, kw = c - kh * 7;
-      const int zh = h + kh - 3, zw = w + kw - 3;
-      const bool in = c < 49 && zh >= 0 && zh < H && zw >= 0 && zw < W;
-      o[i] = to_bits(in ? __ldg(xc + (static_cast<size_t>(d) * H + zh) * W + zw) : 0.f, fmt);
-    }
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(nb) * D * H * W + v) * 64 + g * 8) =
+    for (int i = 0; i < 8; ++i) o[i] = to_bits(off[i] >= 0 ? base[off[i]] : 0.f, fmt);
+    *reinterpret_cast<uint4*>(op + (static_cast<size_t>(h0 + ly) * W + w0 + lx) * 64) =
         *reinterpret_cast<const uint4*>(o);
   }
 }
 
 // dx[d][h][w] = sum_{kh,kw} g[d][h - kh + 3][w - kw + 3][kh * 7 + kw]   (adjoint of im2col49; g bf16)
+// The 56 first channels of the tile's halo rows are staged as 28 words per row; thread = one voxel, 49 conflict-free
+// two-byte gathers, summed kh-major like the plain loop (bitwise the same result).
 __global__ void __launch_bounds__(256)
-col2im49_kernel(const __nv_bfloat16* __restrict__ g, int D, int H, int W, float* __restrict__ dx) {
+col2im49_kernel(const __nv_bfloat16* __restrict__ g, int D, int H, int W, int tiles_y, int tiles_x,
+                float* __restrict__ dx) {
+  using namespace ic;
+  extern __shared__ uint32_t gs[];  // [ROWS][PITCH]
   const int nb = blockIdx.y;
-  const unsigned total = static_cast<unsigned>(D) * H * W;
-  const __nv_bfloat16* gc = g + static_cast<size_t>(nb) * total * 64;
-  for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < total; v += gridDim.x * 256u) {
-    const int w = v % W;
-    const unsigned r = v / W;
-    const int h = r % H, d = r / H;
-    float s = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 7; ++kh) {
-      const int zh = h - kh + 3;
-      if (zh < 0 || zh >= H) continue;
-#pragma unroll
-      for (int kw = 0; kw < 7; ++kw) {
-        const int zw = w - kw + 3;
-        if (zw >= 0 && zw < W)
-          s += __bfloat162float(gc[((static_cast<size_t>(d) * H + zh) * W + zw) * 64 + kh * 7 + kw]);
-      }
-    }
-    dx[static_cast<size_t>(nb) * total + v] = s;
+  const int tx = blockIdx.x % tiles_x;
+  const int r = blockIdx.x / tiles_x;
+  const int d = r / tiles_y, h0 = (r % tiles_y) * TY, w0 = tx * TX;
+  const uint4* gp = reinterpret_cast<const uint4*>(g) + ((static_cast<size_t>(nb) * D + d) * H * W) * 8;
+  // 7 x 16 bytes per halo row, several loads in flight per thread (with one 4-byte load per iteration the staging
+  // loop was a chain of 58 L2 round trips per thread and the kernel no faster than the gather it replaced)
+#pragma unroll 5
+  for (int i = threadIdx.x; i < ROWS * 7; i += 256) {
+    const int row = i / 7, part = i - row * 7;
+    const int zh = h0 + row / HX - 3, zw = w0 + row % HX - 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (zh >= 0 && zh < H && zw >= 0 && zw < W) v = __ldg(gp + (static_cast<size_t>(zh) * W + zw) * 8 + part);
+    uint32_t* dst = gs + row * PITCH + part * 4;
+    dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
   }
+  __syncthreads();
+  const int ly = threadIdx.x / TX, lx = threadIdx.x % TX;
+  if (h0 + ly >= H || w0 + lx >= W) return;
+  float s = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 7; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      const int c = kh * 7 + kw;
+      const uint32_t word = gs[((ly - kh + 6) * HX + lx - kw + 6) * PITCH + (c >> 1)];
+      // bf16 -> fp32 is a 16-bit shift; rows outside the plane were staged as zeros (adding +0 changes nothing)
+      s += __uint_as_float((c & 1) ? (word & 0xFFFF0000u) : (word << 16));
+    }
+  }
+  dx[(static_cast<size_t>(nb) * D + d) * H * W + static_cast<size_t>(h0 + ly) * W + w0 + lx] = s;
 }
 
 // Both stencils below work on tiles of 4 x 8 x 8 voxels staged (with their one-voxel halo) in shared memory; a thread
@@ -248,14 +286,20 @@ stencil1to64_kernel(const float* __restrict__ dout, const float* __restrict__ K,
 }  // namespace
 
 int im2col49(const float* x, int NB, int D, int H, int W, int fmt, void* out, cudaStream_t stream) {
-  if (static_cast<long long>(D) * H * W * 8 >= (1ll << 32)) return set_error("im2col49: volume too large");
-  im2col49_kernel<<<dim3(num_sms() * 8, NB), 256, 0, stream>>>(x, D, H, W, fmt, static_cast<uint16_t*>(out));
+  const int ty = (H + ic::TY - 1) / ic::TY, tx = (W + ic::TX - 1) / ic::TX;
+  if (static_cast<long long>(D) * ty * tx >= (1ll << 31) || NB > 65535) return set_error("im2col49: volume too large");
+  im2col49_kernel<<<dim3(D * ty * tx, NB), 256, 0, stream>>>(x, D, H, W, ty, tx, fmt, static_cast<uint16_t*>(out));
   NC_CUDA(cudaGetLastError());
   return 0;
 }
 int col2im49(const void* g, int NB, int D, int H, int W, float* dx, cudaStream_t stream) {
-  if (static_cast<long long>(D) * H * W >= (1ll << 31)) return set_error("col2im49: volume too large");
-  col2im49_kernel<<<dim3(num_sms() * 8, NB), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), D, H, W, dx);
+  const int ty = (H + ic::TY - 1) / ic::TY, tx = (W + ic::TX - 1) / ic::TX;
+  if (static_cast<long long>(D) * ty * tx >= (1ll << 31) || NB > 65535) return set_error("col2im49: volume too large");
+  static bool attr[64] = {false};
+  if (first_use_on_device(attr))
+    NC_CUDA(cudaFuncSetAttribute(col2im49_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ic::COL2IM_SMEM));
+  col2im49_kernel<<<dim3(D * ty * tx, NB), 256, ic::COL2IM_SMEM, stream>>>(static_cast<const __nv_bfloat16*>(g), D, H,
+                                                                            W, ty, tx, dx);
   NC_CUDA(cudaGetLastError());
   return 0;
 }
