@@ -138,7 +138,8 @@ def _conv_case(cuda, n, cin, cout, h, w, stride, seed):
 # (n, cin, cout, h, w, stride): the five layers of the 'basic' PatchGAN incl. odd image sizes (parity classes of
 # different size in the stride-2 data gradient), the Cout = 1 / Cin = 1 kernels and channel counts off the tile size
 CONV_CASES = [(2, 1, 64, 37, 52, 2), (1, 64, 128, 27, 23, 2), (2, 128, 256, 13, 14, 2), (1, 256, 512, 13, 13, 1),
-              (3, 512, 1, 12, 9, 1), (1, 24, 40, 19, 21, 2), (1, 70, 6, 9, 10, 1)]
+              (3, 512, 1, 12, 9, 1), (1, 24, 40, 19, 21, 2), (1, 70, 6, 9, 10, 1), (1, 1, 8, 9, 11, 1),
+              (2, 16, 1, 10, 9, 2), (1, 1, 1, 6, 7, 2)]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
