@@ -81,6 +81,7 @@ int dice_extract_u8(const uint8_t* vol, int vz0, int vnz, const int* size, const
 // a (sample, channel group) — found with an arrival counter — adds the S slice totals in slice order and writes
 // mean / rstd.  The summation order never depends on scheduling, so results are bitwise repeatable.
 constexpr int FIN_SLICES = 64;
+static_assert(FIN_SLICES % 8 == 0, "the final pass loads eight slice totals at a time");
 
 __global__ void __launch_bounds__(256)
 in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int C, double inv_n, float eps,
@@ -96,9 +97,25 @@ in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int 
   double s = 0.0, q = 0.0;
   if (c < C) {
     const float* p = partial + static_cast<size_t>(nb) * rows * 2 * C;
-    for (long long r = r0 + ty; r < r1; r += 8) {
-      s += static_cast<double>(p[(r * 2) * C + c]);
-      q += static_cast<double>(p[(r * 2 + 1) * C + c]);
+    // four rows' loads in flight per step, added in the same (ascending) order as a plain loop: this kernel sits
+    // between every conv and its consumer, and a rolled loop made it a chain of L2 round trips (26 us per launch)
+    long long r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      float vs[4], vq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vs[u] = __ldg(p + ((r + 8 * u) * 2) * C + c);
+        vq[u] = __ldg(p + ((r + 8 * u) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += static_cast<double>(vs[u]);
+        q += static_cast<double>(vq[u]);
+      }
+    }
+    for (; r < r1; r += 8) {
+      s += static_cast<double>(__ldg(p + (r * 2) * C + c));
+      q += static_cast<double>(__ldg(p + (r * 2 + 1) * C + c));
     }
   }
   ssum[ty][tx] = s;
@@ -128,9 +145,18 @@ in_stats_finalize_kernel(const float* __restrict__ partial, long long rows, int 
     __threadfence();
     double S1 = 0.0, Q1 = 0.0;
     const double* base = slice_tot + (static_cast<size_t>(nb) * S * 2) * C;
-    for (int i = 0; i < S; ++i) {
-      S1 += __ldcg(base + (static_cast<size_t>(i) * 2) * C + c);
-      Q1 += __ldcg(base + (static_cast<size_t>(i) * 2 + 1) * C + c);
+    for (int i0 = 0; i0 < S; i0 += 8) {  // S = FIN_SLICES is a multiple of 8; loads first, adds in slice order
+      double vs[8], vq[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        vs[u] = __ldcg(base + (static_cast<size_t>(i0 + u) * 2) * C + c);
+        vq[u] = __ldcg(base + (static_cast<size_t>(i0 + u) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        S1 += vs[u];
+        Q1 += vq[u];
+      }
     }
     const double mean = S1 * inv_n;
     double var = Q1 * inv_n - mean * mean;
