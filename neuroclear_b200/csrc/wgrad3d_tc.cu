@@ -225,8 +225,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
   const size_t n = static_cast<size_t>(taps) * Cout * Cin;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // eight splits' loads in flight, added in split order (a rolled loop was a chain of up to 49 L2 round trips)
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[k * n + i];
+    int k = 0;
+    for (; k + 8 <= splits; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(partial + (k + u) * n + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < splits; ++k) s += __ldg(partial + k * n + i);
     const int ci = static_cast<int>(i % Cin);
     size_t r = i / Cin;
     const int co = static_cast<int>(r % Cout);
