@@ -319,3 +319,37 @@ def test_input_row_end_covers_every_row_a_cube_range_reads(lib):
                 need = max(need, int(ks.max()) + 1 if ks.size else 0)
             got = sharding.input_row_end(geo, int(c0), int(c1))
             assert need <= got <= size[1], (size, c0, c1, need, got)
+
+
+def test_parity_class_data_gradient_index_math():
+    """The stride-2 data gradient of the PatchGAN convolutions is computed per parity class of the input pixel
+    (csrc/disc2d.cu conv2d_k4_dgrad_s2_kernel): class (h % 2, w % 2) is reached only through the taps kh = (h + 1) % 2
+    (+ 2), kw = (w + 1) % 2 (+ 2), from the output pixel ((h + 1 - kh) / 2, (w + 1 - kw) / 2).  The same index math in
+    numpy against torch's autograd, odd and even image sizes (classes of different size)."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(0)
+    for (cin, cout, H, W) in [(3, 5, 9, 12), (2, 4, 8, 7), (1, 2, 5, 5)]:
+        x = torch.tensor(rng.standard_normal((1, cin, H, W)), dtype=torch.float64, requires_grad=True)
+        w = torch.tensor(rng.standard_normal((cout, cin, 4, 4)), dtype=torch.float64)
+        y = torch.nn.functional.conv2d(x, w, stride=2, padding=1)
+        dy = torch.tensor(rng.standard_normal(tuple(y.shape)), dtype=torch.float64)
+        y.backward(dy)
+        Ho, Wo = y.shape[2:]
+        dx = np.zeros((cin, H, W))
+        dyn, wn = dy.numpy()[0], w.numpy()
+        for cls in range(4):
+            ph, pw = cls >> 1, cls & 1
+            kh0, kw0 = (ph + 1) & 1, (pw + 1) & 1
+            Hq, Wq = (H - ph + 1) // 2, (W - pw + 1) // 2
+            for p in range(Hq * Wq):
+                i, j = divmod(p, Wq)
+                h, ww = 2 * i + ph, 2 * j + pw
+                for tap in range(4):
+                    kh, kw = kh0 + 2 * (tap >> 1), kw0 + 2 * (tap & 1)
+                    th, tw = h + 1 - kh, ww + 1 - kw
+                    assert th % 2 == 0 and tw % 2 == 0
+                    if th < 0 or th // 2 >= Ho or tw < 0 or tw // 2 >= Wo:
+                        continue
+                    dx[:, h, ww] += wn[:, :, kh, kw].T @ dyn[:, th // 2, tw // 2]
+        assert np.abs(dx - x.grad.numpy()[0]).max() <= 1e-12 * max(1.0, np.abs(dx).max())
