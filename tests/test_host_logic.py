@@ -353,3 +353,27 @@ def test_parity_class_data_gradient_index_math():
                         continue
                     dx[:, h, ww] += wn[:, :, kh, kw].T @ dyn[:, th // 2, tw // 2]
         assert np.abs(dx - x.grad.numpy()[0]).max() <= 1e-12 * max(1.0, np.abs(dx).max())
+
+
+def test_three_tf32_products_keep_fp32_accuracy():
+    """The PatchGAN convolutions evaluate an fp32 product as lo*hi + hi*lo + hi*hi with hi = tf32(x), lo = tf32(x - hi)
+    (cvt.rna.tf32: 10 mantissa bits, round half away; csrc/disc2d.cu).  Emulated in numpy: the dropped lo*lo term and
+    the rounding of lo leave ~2^-21 per product, i.e. fp32-level results, where a single TF32 product is 2^-11."""
+    import numpy as np
+
+    def tf32(v):
+        b = v.astype(np.float32).view(np.uint32)
+        return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((64, 4096)).astype(np.float32)
+    b = rng.standard_normal((4096,)).astype(np.float32)
+    ah, bh = tf32(a), tf32(b)
+    al, bl = tf32(a - ah), tf32(b - bh)
+    f64 = lambda v: v.astype(np.float64)
+    exact = f64(a) @ f64(b)
+    three = f64(al) @ f64(bh) + f64(ah) @ f64(bl) + f64(ah) @ f64(bh)
+    one = f64(ah) @ f64(bh)
+    scale = np.abs(f64(a)) @ np.abs(f64(b))
+    assert (np.abs(three - exact) / scale).max() <= 2.0 ** -20
+    assert (np.abs(one - exact) / scale).max() >= 2.0 ** -16      # what a plain TF32 GEMM would give
